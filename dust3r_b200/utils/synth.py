@@ -1,0 +1,92 @@
+"""Deterministic synthetic weights / images / pointmaps.
+
+There are no checkpoints or datasets offline, so tests, goldens and bench.py all draw from here.  Values
+depend only on (key, shape, seed) through torch's CPU Philox-free default generator, which is
+reproducible across machines for a fixed torch version; goldens additionally store the outputs.
+"""
+from __future__ import annotations
+
+import hashlib
+import math
+import torch
+
+from ..config import ModelConfig, state_dict_spec
+
+
+def _gen(seed: int, key: str) -> torch.Generator:
+    h = int.from_bytes(hashlib.sha256(f'{seed}:{key}'.encode()).digest()[:7], 'little')
+    g = torch.Generator(device='cpu')
+    g.manual_seed(h)
+    return g
+
+
+def synth_state_dict(cfg: ModelConfig, seed: int = 0, dtype=torch.float32):
+    """Xavier-like weights (as croco.py:111-127 initialises them) but with non-zero biases and
+    non-unit LayerNorm gains so every epilogue path is exercised.  layer_rn.k aliases layer{k+1}_rn."""
+    sd = {}
+    spec = state_dict_spec(cfg)
+    for key, shape in spec.items():
+        if '.scratch.layer_rn.' in key:
+            continue
+        g = _gen(seed, key)
+        if key == 'mask_token':
+            t = torch.randn(shape, generator=g) * 0.02
+        elif '.norm' in key or key.startswith(('enc_norm', 'dec_norm')):
+            if key.endswith('weight'):
+                t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+            else:
+                t = 0.05 * torch.randn(shape, generator=g)
+        elif key.endswith('bias'):
+            t = 0.02 * torch.randn(shape, generator=g)
+        else:
+            fan_out = shape[0] * (math.prod(shape[2:]) if len(shape) > 2 else 1)
+            fan_in = math.prod(shape[1:])
+            if '.act_postprocess.0.1.' in key or '.act_postprocess.1.1.' in key:
+                # ConvTranspose2d weight is (Cin, Cout, k, k): every output pixel sees Cin taps
+                fan_in, fan_out = shape[0], shape[1]
+            a = math.sqrt(6.0 / (fan_in + fan_out))
+            if key.endswith('.dpt.head.4.weight'):
+                # un-normalised DPT trunk reaches std~8 with xavier weights; trained heads emit O(1)
+                # log-depths, so damp the last 1x1 conv to keep exp()/expm1() in a sane range
+                a *= 0.06
+            t = (torch.rand(shape, generator=g) * 2 - 1) * a
+        sd[key] = t.to(dtype)
+    for key in spec:
+        if '.scratch.layer_rn.' in key:
+            k = int(key.split('.scratch.layer_rn.')[1].split('.')[0])
+            sd[key] = sd[key.replace(f'.scratch.layer_rn.{k}.', f'.scratch.layer{k + 1}_rn.')]
+    return {k: sd[k] for k in spec}
+
+
+def synth_images(n: int, H: int, W: int, seed: int = 0):
+    """n images in [-1,1] (the ImgNorm range, dust3r/utils/image.py:23) in load_images' dict format
+    (utils/image.py:122-123)."""
+    import numpy as np
+    out = []
+    for i in range(n):
+        g = _gen(seed, f'img{i}')
+        # smooth-ish content: low-res noise upsampled + fine noise, clipped to [-1,1]
+        low = torch.rand((1, 3, max(H // 16, 1), max(W // 16, 1)), generator=g) * 2 - 1
+        img = torch.nn.functional.interpolate(low, size=(H, W), mode='bilinear', align_corners=False)
+        img = (img + 0.25 * (torch.rand((1, 3, H, W), generator=g) * 2 - 1)).clamp(-1, 1)
+        out.append(dict(img=img, true_shape=np.int32([[H, W]]), idx=i, instance=str(i)))
+    return out
+
+
+def synth_pair_predictions(n_imgs: int, edges, H: int, W: int, seed: int = 0):
+    """Directly synthesise what inference() would return for `edges` (list of (i,j)), as SURVEY §8d
+    prescribes for the alignment benchmark: pts3d ~ N(0,1)+[0,0,3], conf = 1 + 5*U(0,1)."""
+    E = len(edges)
+    g = _gen(seed, f'pairs{n_imgs}:{E}:{H}x{W}')
+    off = torch.tensor([0.0, 0.0, 3.0])
+    pts1 = torch.randn((E, H, W, 3), generator=g) + off
+    pts2 = torch.randn((E, H, W, 3), generator=g) + off
+    conf1 = 1 + 5 * torch.rand((E, H, W), generator=g)
+    conf2 = 1 + 5 * torch.rand((E, H, W), generator=g)
+    import numpy as np
+    ts = torch.from_numpy(np.int32([[H, W]] * E))
+    view1 = dict(idx=[int(i) for i, j in edges], instance=[str(i) for i, j in edges], true_shape=ts)
+    view2 = dict(idx=[int(j) for i, j in edges], instance=[str(j) for i, j in edges], true_shape=ts)
+    pred1 = dict(pts3d=pts1, conf=conf1)
+    pred2 = dict(pts3d_in_other_view=pts2, conf=conf2)
+    return dict(view1=view1, view2=view2, pred1=pred1, pred2=pred2, loss=None)
