@@ -1,0 +1,335 @@
+"""Scene container + alignment loop driver (API mirror of dust3r/cloud_opt/base_opt.py).
+
+The reference runs `niter` x (python forward over torch ops + autograd + torch.optim.Adam + a
+float(loss) sync).  Here `compute_global_alignment` hands the whole loop to the fused CUDA step
+(csrc/align_step.cu) through AlignEngine; this module only keeps the reference's object model
+(edges, pred_i/pred_j/conf_i/conf_j dictionaries keyed "i_j", im_conf, pw_poses, pw_adaptors,
+state_dict split, getters) so callers written against the reference keep working.
+"""
+from __future__ import annotations
+
+from copy import deepcopy
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ..utils.geometry import inv, geotrf
+from ..utils.image import rgb
+from .commons import (edge_str, ALL_DISTS, NoGradParamDict, get_imshapes, signed_expm1, signed_log1p,
+                      get_conf_trf, unitquat_to_rotmat, rotmat_to_unitquat)
+from .engine import AlignEngine
+
+
+class BasePCOptimizer(nn.Module):
+    """Graph node = image, graph edge = one pairwise prediction (pred1, pred2).
+    Constructor arguments follow base_opt.py:44-53."""
+
+    def __init__(self, *args, **kwargs):
+        if len(args) == 1 and len(kwargs) == 0:
+            other = deepcopy(args[0])
+            attrs = '''edges is_symmetrized dist n_imgs pred_i pred_j imshapes
+                        min_conf_thr conf_thr conf_i conf_j im_conf
+                        base_scale norm_pw_scale POSE_DIM pw_poses
+                        pw_adaptors pw_adaptors has_im_poses rand_pose imgs verbose'''.split()
+            self.__dict__.update({k: other[k] for k in attrs})
+        else:
+            self._init_from_views(*args, **kwargs)
+
+    def _init_from_views(self, view1, view2, pred1, pred2,
+                         dist='l1', conf='log', min_conf_thr=3, base_scale=0.5,
+                         allow_pw_adaptors=False, pw_break=20, rand_pose=torch.randn,
+                         iterationsCount=None, verbose=True):
+        super().__init__()
+        idx1 = view1['idx'] if isinstance(view1['idx'], list) else view1['idx'].tolist()
+        idx2 = view2['idx'] if isinstance(view2['idx'], list) else view2['idx'].tolist()
+        view1['idx'], view2['idx'] = idx1, idx2
+        self.edges = [(int(i), int(j)) for i, j in zip(idx1, idx2)]
+        self.is_symmetrized = set(self.edges) == {(j, i) for i, j in self.edges}
+        if dist not in ALL_DISTS:
+            raise KeyError(dist)
+        self.dist = dist
+        self.verbose = verbose
+        self.n_imgs = self._check_edges()
+
+        pts1, pts2 = pred1['pts3d'], pred2['pts3d_in_other_view']
+        keys = self.str_edges
+        self.pred_i = NoGradParamDict({ij: pts1[n] for n, ij in enumerate(keys)})
+        self.pred_j = NoGradParamDict({ij: pts2[n] for n, ij in enumerate(keys)})
+        self.imshapes = get_imshapes(self.edges, pts1, pts2)
+
+        c1, c2 = pred1['conf'], pred2['conf']
+        self.min_conf_thr = min_conf_thr
+        self.conf_mode = conf
+        self.conf_trf = get_conf_trf(conf)
+        self.conf_i = NoGradParamDict({ij: c1[n] for n, ij in enumerate(keys)})
+        self.conf_j = NoGradParamDict({ij: c2[n] for n, ij in enumerate(keys)})
+        self.im_conf = self._compute_img_conf(c1, c2)
+        for p in self.im_conf:
+            p.requires_grad = False
+
+        self.base_scale = base_scale
+        self.norm_pw_scale = True
+        self.pw_break = pw_break
+        self.POSE_DIM = 7
+        self.pw_poses = nn.Parameter(rand_pose((self.n_edges, 1 + self.POSE_DIM)))
+        self.pw_adaptors = nn.Parameter(torch.zeros((self.n_edges, 2)))
+        self.pw_adaptors.requires_grad_(allow_pw_adaptors)
+        self.has_im_poses = False
+        self.rand_pose = rand_pose
+
+        self.imgs = None
+        if 'img' in view1 and 'img' in view2:
+            imgs = [torch.zeros((3,) + hw) for hw in self.imshapes]
+            for v in range(len(self.edges)):
+                imgs[idx1[v]] = view1['img'][v]
+                imgs[idx2[v]] = view2['img'][v]
+            self.imgs = rgb(imgs)
+        self._engine = None
+
+    # ---------------------------------------------------------------- bookkeeping
+    @property
+    def n_edges(self):
+        return len(self.edges)
+
+    @property
+    def str_edges(self):
+        return [edge_str(i, j) for i, j in self.edges]
+
+    @property
+    def imsizes(self):
+        return [(w, h) for h, w in self.imshapes]
+
+    @property
+    def device(self):
+        return next(iter(self.parameters())).device
+
+    def state_dict(self, trainable=True):
+        every = super().state_dict()
+        observed = ('_', 'pred_i.', 'pred_j.', 'conf_i.', 'conf_j.')
+        return {k: v for k, v in every.items() if k.startswith(observed) != trainable}
+
+    def load_state_dict(self, data):
+        self._engine = None
+        return super().load_state_dict(self.state_dict(trainable=False) | data)
+
+    def _apply(self, fn, *a, **kw):
+        self._engine = None  # device / dtype moves invalidate the packed observation buffer
+        return super()._apply(fn, *a, **kw)
+
+    def _check_edges(self):
+        indices = sorted({i for edge in self.edges for i in edge})
+        assert indices == list(range(len(indices))), 'bad pair indices: missing values '
+        return len(indices)
+
+    @torch.no_grad()
+    def _compute_img_conf(self, pred1_conf, pred2_conf):
+        im_conf = nn.ParameterList([torch.zeros(hw, device=pred1_conf[0].device) for hw in self.imshapes])
+        for e, (i, j) in enumerate(self.edges):
+            im_conf[i] = torch.maximum(im_conf[i], pred1_conf[e])
+            im_conf[j] = torch.maximum(im_conf[j], pred2_conf[e])
+        return im_conf
+
+    # ---------------------------------------------------------------- pairwise poses
+    def get_adaptors(self):
+        adapt = self.pw_adaptors
+        adapt = torch.cat((adapt[:, 0:1], adapt), dim=-1)
+        if self.norm_pw_scale:
+            adapt = adapt - adapt.mean(dim=1, keepdim=True)
+        return (adapt / self.pw_break).exp()
+
+    def _get_poses(self, poses):
+        R = unitquat_to_rotmat(poses[:, :4])
+        T = signed_expm1(poses[:, 4:7])
+        RT = torch.zeros((len(poses), 4, 4), dtype=poses.dtype, device=poses.device)
+        RT[:, :3, :3] = R
+        RT[:, :3, 3] = T
+        RT[:, 3, 3] = 1
+        return RT
+
+    def _set_pose(self, poses, idx, R, T=None, scale=None, force=False):
+        pose = poses[idx]
+        if not (pose.requires_grad or force):
+            return pose
+        if R.shape == (4, 4):
+            assert T is None
+            T = R[:3, 3]
+            R = R[:3, :3]
+        if R is not None:
+            pose.data[0:4] = rotmat_to_unitquat(R).to(pose.device)
+        if T is not None:
+            pose.data[4:7] = signed_log1p(torch.as_tensor(T / (scale or 1), dtype=torch.float32)).to(pose.device)
+        if scale is not None:
+            assert poses.shape[-1] in (8, 13)
+            pose.data[-1] = np.log(float(scale))
+        return pose
+
+    def get_pw_norm_scale_factor(self):
+        if self.norm_pw_scale:
+            return (np.log(self.base_scale) - self.pw_poses[:, -1].mean()).exp()
+        return 1
+
+    def get_pw_scale(self):
+        return self.pw_poses[:, -1].exp() * self.get_pw_norm_scale_factor()
+
+    def get_pw_poses(self):
+        RT = self._get_poses(self.pw_poses)
+        scaled = RT.clone()
+        scaled[:, :3] *= self.get_pw_scale().view(-1, 1, 1)
+        return scaled
+
+    # ---------------------------------------------------------------- accessors
+    def get_masks(self):
+        return [(conf > self.min_conf_thr) for conf in self.im_conf]
+
+    def get_conf(self, mode=None):
+        trf = self.conf_trf if mode is None else get_conf_trf(mode)
+        return [trf(c) for c in self.im_conf]
+
+    def depth_to_pts3d(self):
+        raise NotImplementedError()
+
+    def get_pts3d(self, raw=False):
+        res = self.depth_to_pts3d()
+        if not raw:
+            res = [dm[:h * w].view(h, w, 3) for dm, (h, w) in zip(res, self.imshapes)]
+        return res
+
+    def _set_focal(self, idx, focal, force=False):
+        raise NotImplementedError()
+
+    def get_focals(self):
+        raise NotImplementedError()
+
+    def get_known_focal_mask(self):
+        raise NotImplementedError()
+
+    def get_principal_points(self):
+        raise NotImplementedError()
+
+    def get_im_poses(self):
+        raise NotImplementedError()
+
+    def _set_depthmap(self, idx, depth, force=False):
+        raise NotImplementedError()
+
+    def get_depthmaps(self, raw=False):
+        raise NotImplementedError()
+
+    def clean_pointcloud(self, **kw):
+        cams = inv(self.get_im_poses())
+        K = self.get_intrinsics()
+        depthmaps = self.get_depthmaps()
+        all_pts3d = self.get_pts3d()
+        new_im_confs = clean_pointcloud(self.im_conf, K, cams, depthmaps, all_pts3d, **kw)
+        for i, new_conf in enumerate(new_im_confs):
+            self.im_conf[i].data[:] = new_conf
+        return self
+
+    # ---------------------------------------------------------------- engine plumbing
+    def _engine_variant(self):
+        return 'per_edge'   # BasePCOptimizer.forward (base_opt.py:246-273): per-edge means / n_edges
+
+    def _engine_pix_stride(self):
+        return None
+
+    def _build_engine(self):
+        dev = self.device
+        keys = self.str_edges
+        self._engine = AlignEngine(
+            self.edges, self.imshapes,
+            [self.pred_i[k] for k in keys], [self.pred_j[k] for k in keys],
+            [self.conf_trf(self.conf_i[k]) for k in keys], [self.conf_trf(self.conf_j[k]) for k in keys],
+            device=dev, dist=self.dist, variant=self._engine_variant(), pix_stride=self._engine_pix_stride(),
+            base_scale=self.base_scale, pw_break=self.pw_break,
+            focal_break=getattr(self, 'focal_break', getattr(self, 'focal_brake', 20)))
+        return self._engine
+
+    def _engine_push(self, eng):
+        """copy python-side parameters into the engine buffers; returns a finaliser that copies back"""
+        raise NotImplementedError()
+
+    def _get_engine(self):
+        eng = self._engine if self._engine is not None else self._build_engine()
+        return eng
+
+    def forward(self, ret_details=False):
+        """Objective at the current parameters (a CUDA scalar tensor; no autograd graph — gradients
+        are analytic inside the fused kernel)."""
+        if ret_details:
+            raise NotImplementedError('ret_details is not provided by the fused kernel')
+        eng = self._get_engine()
+        pull = self._engine_push(eng)
+        loss = eng.evaluate_loss()
+        del pull
+        return loss
+
+    @torch.no_grad()
+    def compute_global_alignment(self, init=None, niter_PnP=10, **kw):
+        if init is None:
+            pass
+        elif init in ('msp', 'mst'):
+            from . import init_im_poses as init_fun
+            init_fun.init_minimum_spanning_tree(self, niter_PnP=niter_PnP)
+        elif init == 'known_poses':
+            from . import init_im_poses as init_fun
+            init_fun.init_from_known_poses(self, min_conf_thr=self.min_conf_thr, niter_PnP=niter_PnP)
+        else:
+            raise ValueError(f'bad value for {init=}')
+        return global_alignment_loop(self, **kw)
+
+    @torch.no_grad()
+    def mask_sky(self):
+        raise NotImplementedError('sky segmentation (viz) is outside the two hot paths')
+
+    def show(self, *a, **kw):
+        raise NotImplementedError('visualisation is outside the two hot paths (SURVEY §2 #14)')
+
+
+@torch.no_grad()
+def global_alignment_loop(net, lr=0.01, niter=300, schedule='cosine', lr_min=1e-6):
+    """base_opt.py:326-349.  Returns float(loss of the last iteration)."""
+    if not any(p.requires_grad for p in net.parameters()):
+        return net
+    if net.verbose:
+        print('Global alignement - optimizing for:')
+        print([name for name, value in net.named_parameters() if value.requires_grad])
+    if schedule not in ('cosine', 'linear'):
+        raise ValueError(f'bad lr {schedule=}')
+    eng = net._get_engine()
+    pull = net._engine_push(eng)
+    losses = eng.run(niter, lr=lr, schedule=schedule, lr_min=lr_min)
+    pull()
+    net.last_losses = losses
+    if niter <= 0:
+        return float('inf')
+    loss = float(losses[-1])  # the only host sync of the loop
+    if net.verbose:
+        print(f' final loss={loss:g} after {niter} iterations')
+    return loss
+
+
+@torch.no_grad()
+def clean_pointcloud(im_confs, K, cams, depthmaps, all_pts3d, tol=0.001, bad_conf=0, dbg=()):
+    """Lower the confidence of points that another, more confident view sees *behind* its own depth
+    (base_opt.py:369-405).  O(n^2 P) reprojection test in torch ("next" row f3)."""
+    assert len(im_confs) == len(cams) == len(K) == len(depthmaps) == len(all_pts3d)
+    assert 0 <= tol < 1
+    res = [c.clone() for c in im_confs]
+    all_pts3d = [p.view(*c.shape, 3) for p, c in zip(all_pts3d, im_confs)]
+    depthmaps = [d.view(*c.shape) for d, c in zip(depthmaps, im_confs)]
+    for i, pts3d in enumerate(all_pts3d):
+        for j in range(len(all_pts3d)):
+            if i == j:
+                continue
+            proj = geotrf(cams[j], pts3d)
+            proj_depth = proj[:, :, 2]
+            u, v = geotrf(K[j], proj, norm=1, ncol=2).round().long().unbind(-1)
+            H, W = im_confs[j].shape
+            msk_i = (proj_depth > 0) & (0 <= u) & (u < W) & (0 <= v) & (v < H)
+            msk_j = v[msk_i], u[msk_i]
+            bad_points = (proj_depth[msk_i] < (1 - tol) * depthmaps[j][msk_j]) & (res[i][msk_i] < res[j][msk_j])
+            bad_msk_i = msk_i.clone()
+            bad_msk_i[msk_i] = bad_points
+            res[i][bad_msk_i] = res[i][bad_msk_i].clip_(max=bad_conf)
+    return res

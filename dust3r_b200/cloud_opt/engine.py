@@ -1,0 +1,267 @@
+"""Host driver of the fused alignment kernel (csrc/align_step.cu) — builds the HBM layout the kernel
+streams and launches `d3r_align_run` through the C ABI.
+
+HBM layout (all fp32, owned by torch):
+  obs        float4[ sum over entries P_img ]   (pred.x, pred.y, pred.z, conf_trf(conf)) per pixel;
+             entry = (edge, side); entries of one image are contiguous in a CSR so a CTA walks them
+             while its pixels' world points stay in registers.  32*E*P bytes, read once / iteration.
+  logd       float[ sum_i stride_i ]            log-depth (+ exp_avg, exp_avg_sq): 24*n*P bytes r+w.
+  small      float[ 7n + 2n + 2n + 8E + 2E ]    poses / focals / pp / pairwise poses / adaptors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .commons import cosine_schedule, linear_schedule
+
+
+class AlignEngine:
+    def __init__(self, edges: Sequence[Tuple[int, int]], imshapes: Sequence[Tuple[int, int]],
+                 pred_i: Sequence[torch.Tensor], pred_j: Sequence[torch.Tensor],
+                 weight_i: Sequence[torch.Tensor], weight_j: Sequence[torch.Tensor],
+                 device, dist='l1', variant='stacked', pix_stride=None,
+                 base_scale=0.5, pw_break=20.0, focal_break=20.0):
+        self.device = _lib.require_cuda_device(device)
+        self.lib = _lib.get_lib()
+        self.edges = [(int(i), int(j)) for i, j in edges]
+        self.imshapes = [tuple(map(int, s)) for s in imshapes]
+        self.n, self.E = len(self.imshapes), len(self.edges)
+        n, E = self.n, self.E
+        assert dist in ('l1', 'l2')
+        self.dist, self.variant = dist, variant
+        self.base_scale, self.pw_break, self.focal_break = float(base_scale), float(pw_break), float(focal_break)
+        areas = [h * w for h, w in self.imshapes]
+        self.areas = areas
+        # pixel storage stride per image (PointCloudOptimizer pads every image to max_area,
+        # optimizer.py:37-45; the modular variant packs tightly)
+        self.pix_stride = [int(pix_stride)] * n if pix_stride is not None else areas
+        pix_off = np.zeros(n + 1, dtype=np.int64)
+        pix_off[1:] = np.cumsum(self.pix_stride)
+        self.pix_off = pix_off
+        chunk = self.lib.d3r_align_chunk_pixels()
+        nchunks = [(a + chunk - 1) // chunk for a in areas]
+        chunk_ptr = np.zeros(n + 1, dtype=np.int32)
+        chunk_ptr[1:] = np.cumsum(nchunks)
+        chunk_img = np.repeat(np.arange(n, dtype=np.int32), nchunks)
+        # CSR image -> entries.  entry id order: for each image, incident (edge, side) sorted by edge
+        ent_lists = [[] for _ in range(n)]
+        for e, (i, j) in enumerate(self.edges):
+            ent_lists[i].append((e, 0))
+            ent_lists[j].append((e, 1))
+        ent_ptr = np.zeros(n + 1, dtype=np.int32)
+        ent_ptr[1:] = np.cumsum([len(l) for l in ent_lists])
+        ent_edge = np.zeros(2 * E, dtype=np.int32)
+        ent_obs_off = np.zeros(2 * E, dtype=np.int64)
+        ent_coef = np.zeros(2 * E, dtype=np.float32)
+        edge_ent = np.zeros((E, 2), dtype=np.int32)
+        if variant == 'stacked':     # optimizer.py:59-60,198-199: sum / total_area per side
+            tot = [sum(areas[i] for i, j in self.edges), sum(areas[j] for i, j in self.edges)]
+        k = 0
+        off = 0
+        order = []
+        for img in range(n):
+            for (e, side) in ent_lists[img]:
+                ent_edge[k] = e
+                ent_obs_off[k] = off
+                if variant == 'stacked':
+                    ent_coef[k] = 1.0 / tot[side]
+                else:                # base_opt.py:262-270: mean over pixels, then / n_edges
+                    ent_coef[k] = 1.0 / (areas[img] * E)
+                edge_ent[e, side] = k
+                order.append((e, side, off, areas[img]))
+                off += areas[img]
+                k += 1
+        self.total_obs = off
+        dev = self.device
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        self._img_hw = t(np.int32(self.imshapes))
+        self._pix_off = t(pix_off)
+        self._ent_ptr = t(ent_ptr)
+        self._chunk_ptr = t(chunk_ptr)
+        self._chunk_img = t(chunk_img)
+        self._ent_edge = t(ent_edge)
+        self._ent_obs_off = t(ent_obs_off)
+        self._ent_coef = t(ent_coef)
+        self._edge_ent = t(edge_ent)
+        self.n_chunks = int(chunk_ptr[-1])
+        self.max_chunks = int(max(nchunks))
+        self.max_deg = int(max(len(l) for l in ent_lists))
+        # observations
+        self.obs = torch.empty((self.total_obs, 4), dtype=torch.float32, device=dev)
+        sp = _lib.stream_ptr()
+        for (e, side, o, area) in order:
+            pts = (pred_i if side == 0 else pred_j)[e]
+            w = (weight_i if side == 0 else weight_j)[e]
+            pts = pts.reshape(-1, 3)[:area].to(dev, torch.float32).contiguous()
+            w = w.reshape(-1)[:area].to(dev, torch.float32).contiguous()
+            _lib.check(self.lib.d3r_align_pack_obs(pts.data_ptr(), w.data_ptr(), self.obs.data_ptr(), o, area, sp))
+        nws = self.lib.d3r_align_workspace_floats(n, E, self.n_chunks, self.max_chunks)
+        self.workspace = torch.zeros((nws,), dtype=torch.float32, device=dev)
+        self.counters = torch.zeros((n + 2,), dtype=torch.int32, device=dev)
+        self.n_small = 11 * n + 10 * E
+        self.small = torch.zeros((self.n_small,), dtype=torch.float32, device=dev)
+        self.small_m = torch.zeros_like(self.small)
+        self.small_v = torch.zeros_like(self.small)
+        self.small_trainable = torch.zeros((self.n_small,), dtype=torch.uint8, device=dev)
+        self.logd = None
+        self.logd_m = self.logd_v = None
+        self.sched = torch.zeros((1, 4), dtype=torch.float32, device=dev)
+        self.loss_out = torch.zeros((1,), dtype=torch.float32, device=dev)
+        self.norm_pw_scale = True
+        self.tied_focal = True
+
+    # ------------------------------------------------------------------ parameters
+    def algorithmic_bytes_per_iter(self):
+        """32*E*P (observations read once) + 24*n*P (log-depth + 2 moments r/w)."""
+        return 16 * self.total_obs + 24 * sum(self.areas)
+
+    def _offsets(self):
+        n, E = self.n, self.E
+        o = dict(poses=0, focals=7 * n, pp=9 * n, pw=11 * n, adapt=11 * n + 8 * E)
+        return o
+
+    def set_params(self, logd: torch.Tensor, im_poses, im_focals, im_pp, pw_poses, pw_adaptors,
+                   train_poses, train_focals, train_pp, train_pw=True, train_adaptors=False,
+                   norm_pw_scale=True):
+        """logd: flat float32 CUDA tensor the kernel updates IN PLACE (length pix_off[-1]).
+        im_focals: (n,1) tied or (n,2).  train_*: bool or per-image bool arrays."""
+        n, E = self.n, self.E
+        dev = self.device
+        assert logd.is_cuda and logd.dtype == torch.float32 and logd.is_contiguous() and logd.numel() == int(self.pix_off[-1])
+        self.logd = logd
+        o = self._offsets()
+        f = torch.as_tensor(im_focals, dtype=torch.float32, device=dev).reshape(n, -1)
+        self.tied_focal = f.shape[1] == 1
+        f2 = f.expand(n, 2) if self.tied_focal else f
+        s = self.small
+        s[o['poses']:o['focals']] = torch.as_tensor(im_poses, dtype=torch.float32, device=dev).reshape(-1)
+        s[o['focals']:o['pp']] = f2.reshape(-1)
+        s[o['pp']:o['pw']] = torch.as_tensor(im_pp, dtype=torch.float32, device=dev).reshape(-1)
+        s[o['pw']:o['adapt']] = torch.as_tensor(pw_poses, dtype=torch.float32, device=dev).reshape(-1)
+        s[o['adapt']:] = torch.as_tensor(pw_adaptors, dtype=torch.float32, device=dev).reshape(-1)
+
+        def mask(flag, width):
+            m = np.asarray(flag, dtype=bool)
+            if m.ndim == 0:
+                m = np.full((n,), bool(m))
+            return np.repeat(m.astype(np.uint8)[:, None], width, axis=1).reshape(-1)
+        tr = np.zeros((self.n_small,), dtype=np.uint8)
+        tr[o['poses']:o['focals']] = mask(train_poses, 7)
+        tr[o['focals']:o['pp']] = mask(train_focals, 2)
+        tr[o['pp']:o['pw']] = mask(train_pp, 2)
+        tr[o['pw']:o['adapt']] = 1 if train_pw else 0
+        tr[o['adapt']:] = 1 if train_adaptors else 0
+        self.small_trainable.copy_(torch.from_numpy(tr))
+        self.norm_pw_scale = bool(norm_pw_scale)
+        self._prepared = False
+
+    def get_small(self):
+        n, E = self.n, self.E
+        o = self._offsets()
+        s = self.small
+        f = s[o['focals']:o['pp']].reshape(n, 2)
+        return dict(im_poses=s[o['poses']:o['focals']].reshape(n, 7).clone(),
+                    im_focals=(f[:, :1] if self.tied_focal else f).clone(),
+                    im_pp=s[o['pp']:o['pw']].reshape(n, 2).clone(),
+                    pw_poses=s[o['pw']:o['adapt']].reshape(E, 8).clone(),
+                    pw_adaptors=s[o['adapt']:].reshape(E, 2).clone())
+
+    def reset_adam(self):
+        self.small_m.zero_()
+        self.small_v.zero_()
+        self.logd_m = torch.zeros_like(self.logd)
+        self.logd_v = torch.zeros_like(self.logd)
+
+    # ------------------------------------------------------------------ launches
+    def _desc(self, eval_only=False):
+        d = _lib.AlignDesc()
+        d.n_imgs, d.n_edges, d.n_entries, d.n_chunks = self.n, self.E, 2 * self.E, self.n_chunks
+        d.max_deg, d.max_chunks = self.max_deg, self.max_chunks
+        d.dist_l2 = 1 if self.dist == 'l2' else 0
+        d.norm_pw_scale = int(self.norm_pw_scale)
+        d.tied_focal = int(self.tied_focal)
+        d.eval_only = int(eval_only)
+        d.base_scale, d.pw_break, d.focal_break = self.base_scale, self.pw_break, self.focal_break
+        d.adam_eps, d.beta1, d.beta2 = 1e-8, 0.9, 0.9     # base_opt.py:337
+        d.img_hw = self._img_hw.data_ptr()
+        d.img_pix_off = self._pix_off.data_ptr()
+        d.img_ent_ptr = self._ent_ptr.data_ptr()
+        d.img_chunk_ptr = self._chunk_ptr.data_ptr()
+        d.chunk_img = self._chunk_img.data_ptr()
+        d.ent_edge = self._ent_edge.data_ptr()
+        d.ent_obs_off = self._ent_obs_off.data_ptr()
+        d.ent_coef = self._ent_coef.data_ptr()
+        d.edge_ent = self._edge_ent.data_ptr()
+        d.obs = self.obs.data_ptr()
+        d.logd = self.logd.data_ptr()
+        if self.logd_m is None:
+            self.reset_adam()
+        d.logd_m, d.logd_v = self.logd_m.data_ptr(), self.logd_v.data_ptr()
+        d.small, d.small_m, d.small_v = self.small.data_ptr(), self.small_m.data_ptr(), self.small_v.data_ptr()
+        d.small_trainable = self.small_trainable.data_ptr()
+        d.workspace = self.workspace.data_ptr()
+        d.sched = self.sched.data_ptr()
+        d.loss_out = self.loss_out.data_ptr()
+        d.counters = self.counters.data_ptr()
+        return d
+
+    def prepare(self):
+        d = self._desc()
+        _lib.check(self.lib.d3r_align_prepare(C.byref(d), _lib.stream_ptr()))
+        self._prepared = True
+
+    @staticmethod
+    def make_schedule(niter, lr, schedule='cosine', lr_min=1e-6, beta1=0.9, beta2=0.9, first_step=1):
+        """Per-iteration scalars computed in double exactly as base_opt.py:352-360 + torch Adam do."""
+        rows = np.zeros((max(niter, 1), 4), dtype=np.float64)
+        for it in range(niter):
+            t = it / niter
+            if schedule == 'cosine':
+                cur = cosine_schedule(t, lr, lr_min)
+            elif schedule == 'linear':
+                cur = linear_schedule(t, lr, lr_min)
+            else:
+                raise ValueError(f'bad lr {schedule=}')
+            step = first_step + it
+            bc1 = 1 - beta1 ** step
+            bc2 = 1 - beta2 ** step
+            rows[it] = (cur, cur / bc1, math.sqrt(bc2), 0.0)
+        return rows.astype(np.float32)
+
+    def run(self, niter, lr=0.01, schedule='cosine', lr_min=1e-6, reset_adam=True):
+        """Runs `niter` fused iterations; returns the per-iteration losses as a CUDA tensor
+        (no host sync inside — the reference syncs every iteration via float(loss), base_opt.py:366)."""
+        if reset_adam or self.logd_m is None:
+            self.reset_adam()
+        if niter <= 0:
+            return torch.zeros((0,), dtype=torch.float32, device=self.device)
+        self.sched = torch.from_numpy(self.make_schedule(niter, lr, schedule, lr_min)).to(self.device)
+        self.loss_out = torch.zeros((niter,), dtype=torch.float32, device=self.device)
+        if not getattr(self, '_prepared', False):
+            self.prepare()
+        d = self._desc()
+        _lib.check(self.lib.d3r_align_run(C.byref(d), 0, niter, _lib.stream_ptr()))
+        return self.loss_out
+
+    def evaluate_loss(self):
+        """net.forward(): the objective at the current parameters, nothing updated."""
+        self.sched = torch.zeros((1, 4), dtype=torch.float32, device=self.device)
+        self.loss_out = torch.zeros((1,), dtype=torch.float32, device=self.device)
+        self.prepare()
+        d = self._desc(eval_only=True)
+        _lib.check(self.lib.d3r_align_run(C.byref(d), 0, 1, _lib.stream_ptr()))
+        return self.loss_out[0]
+
+    def pts3d(self):
+        """(sum stride_i, 3) world points of every image's pixels."""
+        self.prepare()
+        out = torch.zeros((int(self.pix_off[-1]), 3), dtype=torch.float32, device=self.device)
+        d = self._desc()
+        _lib.check(self.lib.d3r_align_pts3d(C.byref(d), out.data_ptr(), _lib.stream_ptr()))
+        return out

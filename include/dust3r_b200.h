@@ -1,0 +1,128 @@
+/*
+ * dust3r_b200 — C ABI of the B200-native DUSt3R hot paths (sm_100a).
+ *
+ * The reference (naver/dust3r) has no FFI/plugin registry; its only native entry point is the
+ * pybind function `curope.rope_2d` (croco/models/curope/curope.cpp:49-69).  Everything else on
+ * the two hot paths is Python calling torch.  This header is therefore the boundary a
+ * maintainer binds with ctypes: plain pointers + sizes + a cudaStream_t,
+ * int return codes, no torch / ATen / Python types.
+ *
+ * Conventions
+ *   - every pointer marked `dev` is a CUDA device pointer owned by the caller (PyTorch owns all
+ *     memory; the library never allocates caller-visible memory);
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - return value 0 = success, negative = error; d3r_last_error() gives the message of the
+ *     last failure on the calling thread;
+ *   - calls are asynchronous w.r.t. the host unless stated; thread-safe for distinct streams.
+ */
+#ifndef DUST3R_B200_H_
+#define DUST3R_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define D3R_OK 0
+#define D3R_ERR_INVALID (-1)   /* bad argument / unsupported shape   */
+#define D3R_ERR_CUDA (-2)      /* CUDA runtime / driver error        */
+#define D3R_ERR_UNSUPPORTED_DEVICE (-3)
+
+const char* d3r_last_error(void);
+/* ABI version of this header; bumped on any signature change. */
+int d3r_abi_version(void);
+/* 0 when the current device is sm_100 (B200); D3R_ERR_UNSUPPORTED_DEVICE otherwise. */
+int d3r_check_device(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Path 2 — global alignment (replaces the body of global_alignment_iter(),
+ * dust3r/cloud_opt/base_opt.py:352-366: zero_grad + PointCloudOptimizer.forward
+ * (optimizer.py:188-201) or BasePCOptimizer.forward (base_opt.py:246-273) + loss.backward() +
+ * torch.optim.Adam.step(), for every iteration of global_alignment_loop, base_opt.py:326-349).
+ *
+ * One launch per iteration: unproject depth -> 3D, confidence-weighted pairwise distance,
+ * analytic backward, Adam on the per-pixel log-depths; the last CTA folds the per-edge /
+ * per-image partial sums into pose / focal / principal-point / pairwise-pose gradients, applies
+ * Adam to them and refreshes the transforms for the next launch.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Small parameters live in ONE float buffer `small` (and two more of the same layout for Adam's
+ * exp_avg / exp_avg_sq, plus a uint8 buffer of trainable flags):
+ *   [ im_poses n*7 | im_focals n*2 | im_pp n*2 | pw_poses E*8 | pw_adaptors E*2 ]
+ * im_poses / pw_poses rows are [qx,qy,qz,qw, tx,ty,tz(, log_scale)] exactly as
+ * optimizer.py:30 / base_opt.py:90 store them; im_focals holds focal_break*log(f) twice when the
+ * model has a single focal (fx == fy, tied). */
+typedef struct d3r_align_desc {
+  int32_t n_imgs;          /* n                                                             */
+  int32_t n_edges;         /* E (directed edges, base_opt.py:61)                            */
+  int32_t n_entries;       /* 2*E : one entry per (edge, side)                              */
+  int32_t n_chunks;        /* total CTAs = sum_i ceil(P_i / d3r_align_chunk_pixels())       */
+  int32_t max_deg;         /* max entries incident to one image                             */
+  int32_t max_chunks;      /* max CTAs of one image                                         */
+  int32_t dist_l2;         /* 0: l1_dist, 1: l2_dist (commons.py:62-70)                     */
+  int32_t norm_pw_scale;   /* base_opt.py:86,178-184                                        */
+  int32_t tied_focal;      /* 1: one focal per image (fx==fy), 0: fx_and_fy                 */
+  int32_t eval_only;       /* 1: only write the loss (net.forward()), no parameter update   */
+  float base_scale;        /* base_opt.py:49                                                */
+  float pw_break;          /* base_opt.py:51                                                */
+  float focal_break;       /* optimizer.py:22 / modular_optimizer.py:24 (focal_brake)       */
+  float adam_eps;          /* 1e-8                                                          */
+  float beta1, beta2;      /* (0.9, 0.9) base_opt.py:337                                    */
+
+  /* per image (dev) */
+  const int32_t* img_hw;        /* [n][2] = H, W                                            */
+  const int64_t* img_pix_off;   /* [n+1] offset of image i's pixels in logd / adam buffers  */
+  const int32_t* img_ent_ptr;   /* [n+1] CSR into the entry arrays                          */
+  const int32_t* img_chunk_ptr; /* [n+1] first CTA index of image i                         */
+  /* per CTA (dev) */
+  const int32_t* chunk_img;     /* [n_chunks] image handled by CTA c                        */
+  /* per entry, CSR order (dev) */
+  const int32_t* ent_edge;      /* [2E] edge id                                             */
+  const int64_t* ent_obs_off;   /* [2E] offset (in float4) of the entry's observations      */
+  const float*   ent_coef;      /* [2E] loss coefficient: 1/total_area (stacked) or 1/(P*E) */
+  const int32_t* edge_ent;      /* [E][2] entry index of (edge, side i) and (edge, side j)  */
+  /* observations (dev): float4 = (pred.x, pred.y, pred.z, weight) per pixel per entry.
+   * 32*E*P bytes in total = the read-once traffic of SURVEY §8d.                          */
+  const void* obs;
+
+  /* trainable state (dev) */
+  float* logd;                  /* [sum P_i] log-depth, optimizer.py:29                     */
+  float* logd_m;                /* Adam exp_avg                                             */
+  float* logd_v;                /* Adam exp_avg_sq                                          */
+  float* small;                 /* layout above                                             */
+  float* small_m;
+  float* small_v;
+  const uint8_t* small_trainable; /* same layout, 1 = requires_grad                         */
+
+  /* derived per-iteration state + scratch (dev), sizes from d3r_align_workspace_floats()  */
+  float* workspace;
+  /* [niter_total][4] = lr, lr/bias_correction1, sqrt(bias_correction2), 0 for every step   */
+  const float* sched;
+  float* loss_out;              /* [niter_total] loss of every iteration                    */
+  int32_t* counters;            /* [n + 2] zero-initialised by the caller once              */
+} d3r_align_desc;
+
+/* sizeof(d3r_align_desc) as compiled into the library (binding self-check). */
+int d3r_sizeof_align_desc(void);
+/* Pixels handled by one CTA of the alignment kernel (a compile-time constant of the library). */
+int d3r_align_chunk_pixels(void);
+/* Number of floats of `workspace` needed for a problem of this size. */
+int64_t d3r_align_workspace_floats(int32_t n_imgs, int32_t n_edges, int32_t n_chunks, int32_t max_chunks);
+/* Computes the transforms used by the first iteration from `small` (call once after the
+ * parameters are (re)initialised or modified from the host). */
+int d3r_align_prepare(const d3r_align_desc* desc, void* stream);
+/* Runs iterations [it_begin, it_end) (indices into sched / loss_out).  Asynchronous. */
+int d3r_align_run(const d3r_align_desc* desc, int32_t it_begin, int32_t it_end, void* stream);
+/* World-frame pointmaps X[i] = R_i * unproject(depth_i) + T_i for every image
+ * (PointCloudOptimizer.depth_to_pts3d, optimizer.py:170-180).  out: [sum P_i][3] float. */
+int d3r_align_pts3d(const d3r_align_desc* desc, float* out_dev, void* stream);
+/* Packs pred (P,3) + weight (P) rows into the float4 observation layout. */
+int d3r_align_pack_obs(const float* pts_dev, const float* weight_dev, void* obs_dev, int64_t obs_off,
+                       int64_t n_pix, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DUST3R_B200_H_ */

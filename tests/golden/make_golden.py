@@ -1,0 +1,151 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on CPU fp32.
+
+    python tests/golden/make_golden.py            # in the build container (reference mounted)
+
+Forward goldens come from the pure reference.  Alignment goldens are "reference cloud_opt + local roma
+restatement" (oracle/roma_stub) because `roma` is not installable offline.
+Inputs/weights are regenerated from dust3r_b200.utils.synth by the tests (deterministic), so the
+fixtures only hold the reference's OUTPUTS plus input checksums.
+"""
+import copy
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, 'oracle', 'roma_stub'))
+sys.path.insert(0, '/root/reference')
+sys.path.insert(0, ROOT)
+
+from dust3r_b200.config import ModelConfig, vitl_512_dpt, vitl_224_linear  # noqa: E402
+from dust3r_b200.utils.synth import synth_state_dict, synth_images, synth_pair_predictions  # noqa: E402
+
+inf = float('inf')
+
+
+def ref_model(cfg):
+    from dust3r.model import AsymmetricCroCo3DStereo
+    m = AsymmetricCroCo3DStereo(
+        pos_embed=cfg.pos_embed, patch_embed_cls='PatchEmbedDust3R', img_size=cfg.img_size, head_type=cfg.head_type,
+        output_mode='pts3d', depth_mode=cfg.depth_mode, conf_mode=cfg.conf_mode, enc_embed_dim=cfg.enc_embed_dim,
+        enc_depth=cfg.enc_depth, enc_num_heads=cfg.enc_num_heads, dec_embed_dim=cfg.dec_embed_dim,
+        dec_depth=cfg.dec_depth, dec_num_heads=cfg.dec_num_heads, landscape_only=cfg.landscape_only).eval()
+    return m
+
+
+SMALL = dict(
+    small_dpt=(ModelConfig(img_size=(96, 96), enc_embed_dim=128, enc_depth=2, enc_num_heads=2, dec_embed_dim=128,
+                           dec_depth=12, dec_num_heads=2, head_type='dpt', landscape_only=False), 64, 96),
+    small_linear=(ModelConfig(img_size=(96, 96), enc_embed_dim=192, enc_depth=3, enc_num_heads=3, dec_embed_dim=128,
+                              dec_depth=2, dec_num_heads=2, head_type='linear', landscape_only=False), 80, 64),
+)
+
+
+def forward_goldens():
+    from dust3r.inference import inference
+    from dust3r.image_pairs import make_pairs
+    for name, (cfg, H, W) in SMALL.items():
+        torch.manual_seed(0)
+        m = ref_model(cfg)
+        sd = synth_state_dict(cfg, seed=11)
+        m.load_state_dict(sd, strict=True)
+        imgs = synth_images(3, H, W, seed=5)
+        pairs = make_pairs(imgs, scene_graph='complete', prefilter=None, symmetrize=True)   # 6 pairs
+        out = inference(pairs, m, 'cpu', batch_size=4, verbose=False)
+        np.savez_compressed(os.path.join(HERE, f'forward_{name}.npz'),
+                            pts3d=out['pred1']['pts3d'].numpy(), conf1=out['pred1']['conf'].numpy(),
+                            pts3d_in_other_view=out['pred2']['pts3d_in_other_view'].numpy(),
+                            conf2=out['pred2']['conf'].numpy(),
+                            idx1=np.int64(out['view1']['idx']), idx2=np.int64(out['view2']['idx']),
+                            img_sum=np.float64([float(i['img'].double().sum()) for i in imgs]))
+        print('wrote', name, out['pred1']['pts3d'].shape)
+
+    # the two published architectures, one 1-pair batch each, strided sample of the outputs
+    for name, cfg, H, W, stride in (('vitl_512_dpt', vitl_512_dpt(), 384, 512, 8), ('vitl_224_linear', vitl_224_linear(), 224, 224, 4)):
+        m = ref_model(cfg)
+        sd = synth_state_dict(cfg, seed=0)
+        m.load_state_dict(sd, strict=True)
+        imgs = synth_images(2, H, W, seed=3)
+        out = inference([(imgs[0], imgs[1])], m, 'cpu', batch_size=1, verbose=False)
+        s = stride
+        np.savez_compressed(os.path.join(HERE, f'forward_{name}.npz'), stride=s,
+                            pts3d=out['pred1']['pts3d'][:, ::s, ::s].numpy(), conf1=out['pred1']['conf'][:, ::s, ::s].numpy(),
+                            pts3d_in_other_view=out['pred2']['pts3d_in_other_view'][:, ::s, ::s].numpy(),
+                            conf2=out['pred2']['conf'][:, ::s, ::s].numpy(),
+                            mean_abs=np.float64([out['pred1']['pts3d'].abs().mean(), out['pred1']['conf'].mean(),
+                                                 out['pred2']['pts3d_in_other_view'].abs().mean(), out['pred2']['conf'].mean()]))
+        print('wrote', name)
+
+
+def pair_goldens():
+    from dust3r.image_pairs import make_pairs
+    res = {}
+    for n in (2, 3, 8, 50):
+        imgs = [dict(idx=i, instance=str(i)) for i in range(n)]
+        for sg in ('complete', 'swin-3', 'swin-5-noncyclic', 'logwin-3', 'logwin-4-noncyclic', 'oneref-0', 'oneref-1'):
+            for sym in (True, False):
+                for pf in (None, 'seq3', 'cyc3'):
+                    pairs = make_pairs(imgs, scene_graph=sg, prefilter=pf, symmetrize=sym)
+                    res[f'{n}|{sg}|{int(sym)}|{pf}'] = np.int32([(a['idx'], b['idx']) for a, b in pairs]).reshape(-1, 2)
+    np.savez_compressed(os.path.join(HERE, 'make_pairs.npz'), **res)
+    print('wrote make_pairs', len(res))
+
+
+def align_goldens():
+    from dust3r.cloud_opt import global_aligner, GlobalAlignerMode
+    from dust3r.cloud_opt.base_opt import global_alignment_iter
+    from oracle.align_oracle import AlignProblem, init_params
+    n, H, W = 4, 24, 32
+    edges = [(i, j) for i in range(n) for j in range(i)]
+    edges = edges + [(j, i) for i, j in edges]
+    res = {}
+    for mode, variant in ((GlobalAlignerMode.PointCloudOptimizer, 'stacked'), (GlobalAlignerMode.ModularPointCloudOptimizer, 'per_edge')):
+        for dist in ('l1', 'l2'):
+            for schedule in ('cosine', 'linear'):
+                out = synth_pair_predictions(n, edges, H, W, seed=1)
+                net = global_aligner(copy.deepcopy(out), 'cpu', mode=mode, verbose=False, dist=dist)
+                prob = AlignProblem.from_output(out, dist=dist, variant=variant)
+                P0 = init_params(prob, seed=5)
+                with torch.no_grad():
+                    if variant == 'stacked':
+                        net.im_depthmaps.data[:] = torch.stack(P0['im_depthmaps'])
+                        net.im_poses.data[:] = P0['im_poses']
+                        net.im_focals.data[:] = P0['im_focals']
+                    else:
+                        for i in range(n):
+                            net.im_depthmaps[i].data[:] = P0['im_depthmaps'][i].view(H, W)
+                            net.im_poses[i].data[:] = P0['im_poses'][i]
+                            net.im_focals[i].data[:] = P0['im_focals'][i]
+                    net.pw_poses.data[:] = P0['pw_poses']
+                niter = 60
+                params = [p for p in net.parameters() if p.requires_grad]
+                opt = torch.optim.Adam(params, lr=0.01, betas=(0.9, 0.9))
+                losses = [global_alignment_iter(net, it, niter, 0.01, 1e-6, opt, schedule)[0] for it in range(niter)]
+                key = f'{variant}|{dist}|{schedule}'
+                res[key + '|loss'] = np.float32(losses)
+                if variant == 'stacked':
+                    res[key + '|depth'] = net.im_depthmaps.detach().numpy()
+                    res[key + '|poses'] = net.im_poses.detach().numpy()
+                    res[key + '|focals'] = net.im_focals.detach().numpy()
+                else:
+                    res[key + '|depth'] = torch.stack([d.detach().reshape(-1) for d in net.im_depthmaps]).numpy()
+                    res[key + '|poses'] = torch.stack([d.detach() for d in net.im_poses]).numpy()
+                    res[key + '|focals'] = torch.stack([d.detach() for d in net.im_focals]).numpy()
+                res[key + '|pw'] = net.pw_poses.detach().numpy()
+                print(key, losses[0], losses[-1])
+    np.savez_compressed(os.path.join(HERE, 'align_n4.npz'), **res)
+
+
+if __name__ == '__main__':
+    what = sys.argv[1:] or ['pairs', 'align', 'forward']
+    with torch.no_grad():
+        if 'pairs' in what:
+            pair_goldens()
+    if 'align' in what:
+        align_goldens()
+    with torch.no_grad():
+        if 'forward' in what:
+            forward_goldens()

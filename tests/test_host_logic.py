@@ -1,0 +1,103 @@
+"""CPU tests of the host-side mirror of the reference API (no GPU, no compute through the .so)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, has_reference
+from dust3r_b200.config import vitl_512_dpt, vitl_224_linear, state_dict_spec
+from dust3r_b200.image_pairs import make_pairs
+
+
+@pytest.mark.parametrize('name,cfg', [('dpt512', vitl_512_dpt()), ('lin224', vitl_224_linear())])
+def test_state_dict_layout_matches_reference(name, cfg):
+    ref = json.load(open(os.path.join(GOLDEN, f'ref_state_dict_{name}.json')))
+    spec = state_dict_spec(cfg)
+    assert list(ref.keys()) == list(spec.keys())
+    for k in ref:
+        assert tuple(ref[k]) == tuple(spec[k]), k
+
+
+def test_make_pairs_bit_exact_against_reference_golden():
+    gold = np.load(os.path.join(GOLDEN, 'make_pairs.npz'))
+    assert len(gold.files) == 168
+    for key in gold.files:
+        n, sg, sym, pf = key.split('|')
+        imgs = [dict(idx=i, instance=str(i)) for i in range(int(n))]
+        pairs = make_pairs(imgs, scene_graph=sg, prefilter=None if pf == 'None' else pf, symmetrize=bool(int(sym)))
+        got = np.int32([(a['idx'], b['idx']) for a, b in pairs]).reshape(-1, 2)
+        assert got.shape == gold[key].shape, key
+        assert (got == gold[key]).all(), key
+
+
+def test_make_pairs_counts():
+    imgs = [dict(idx=i, instance=str(i)) for i in range(8)]
+    assert len(make_pairs(imgs, symmetrize=False)) == 28
+    assert len(make_pairs(imgs, symmetrize=True)) == 56
+    imgs = [dict(idx=i, instance=str(i)) for i in range(50)]
+    assert len(make_pairs(imgs, symmetrize=False)) == 1225
+
+
+def test_rotation_helpers_roundtrip():
+    from dust3r_b200.cloud_opt.commons import unitquat_to_rotmat, rotmat_to_unitquat, rigid_points_registration
+    g = torch.Generator().manual_seed(0)
+    q = torch.randn((64, 4), generator=g)
+    R = unitquat_to_rotmat(q)
+    assert torch.allclose(R @ R.transpose(-1, -2), torch.eye(3).expand(64, 3, 3), atol=1e-5)
+    q2 = rotmat_to_unitquat(R)
+    assert torch.allclose(unitquat_to_rotmat(q2), R, atol=1e-5)
+    x = torch.randn((500, 3), generator=g)
+    s, t = 1.7, torch.tensor([0.3, -2.0, 1.0])
+    y = s * x @ R[0].T + t
+    Rr, tr, sr = rigid_points_registration(x, y, weights=torch.rand(500, generator=g) + 0.1, compute_scaling=True)
+    assert torch.allclose(Rr, R[0], atol=1e-4) and torch.allclose(tr, t, atol=1e-4) and abs(float(sr) - s) < 1e-4
+
+
+def test_optimizer_host_objects_on_cpu():
+    """Construction, parametrisation and getters work without a GPU; the optimisation itself must
+    refuse to run anywhere but on a B200 (no CPU fallback)."""
+    from dust3r_b200.cloud_opt import global_aligner, GlobalAlignerMode
+    from dust3r_b200.utils.synth import synth_pair_predictions
+    from dust3r_b200._lib import D3RError
+    n, H, W = 3, 16, 32
+    edges = [(i, j) for i in range(n) for j in range(i)]
+    out = synth_pair_predictions(n, edges, H, W, seed=2)
+    torch.manual_seed(0)
+    net = global_aligner(out, 'cpu', mode=GlobalAlignerMode.PointCloudOptimizer, verbose=False)
+    assert net.im_depthmaps.shape == (n, H * W) and net.im_poses.shape == (n, 7)
+    assert net.im_focals.shape == (n, 1) and net.pw_poses.shape == (len(edges), 8)
+    assert abs(float(net.get_focals()[0]) - max(H, W)) < 1e-3
+    assert net.get_im_poses().shape == (n, 4, 4)
+    assert [tuple(p.shape) for p in net.get_pts3d()] == [(H, W, 3)] * n
+    sd = net.state_dict()
+    assert set(sd) == {'pw_poses', 'pw_adaptors', 'im_depthmaps', 'im_poses', 'im_focals', 'im_pp'} | {f'im_conf.{i}' for i in range(n)}
+    with pytest.raises(D3RError):
+        net.compute_global_alignment(init=None, niter=2)
+    net2 = global_aligner(out, 'cpu', mode=GlobalAlignerMode.ModularPointCloudOptimizer, verbose=False)
+    assert len(net2.im_depthmaps) == n and net2.get_intrinsics().shape == (n, 3, 3)
+
+
+@pytest.mark.skipif(not has_reference(), reason='reference not mounted')
+def test_optimizer_init_matches_reference_draws():
+    """Same torch seed -> same initial parameters as the reference constructor (optimizer.py:29-33)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), '..', 'oracle', 'roma_stub'))
+    sys.path.insert(0, '/root/reference')
+    import copy
+    from dust3r.cloud_opt import global_aligner as ref_aligner, GlobalAlignerMode as RefMode
+    from dust3r_b200.cloud_opt import global_aligner, GlobalAlignerMode
+    from dust3r_b200.utils.synth import synth_pair_predictions
+    n, H, W = 3, 16, 32
+    edges = [(i, j) for i in range(n) for j in range(i)]
+    out = synth_pair_predictions(n, edges, H, W, seed=2)
+    torch.manual_seed(123)
+    ref = ref_aligner(copy.deepcopy(out), 'cpu', mode=RefMode.PointCloudOptimizer, verbose=False)
+    torch.manual_seed(123)
+    net = global_aligner(copy.deepcopy(out), 'cpu', mode=GlobalAlignerMode.PointCloudOptimizer, verbose=False)
+    for k in ('pw_poses', 'im_depthmaps', 'im_poses', 'im_focals', 'im_pp'):
+        assert torch.equal(getattr(ref, k).data, getattr(net, k).data), k
+    for a, b in zip(ref.get_pts3d(), net.get_pts3d()):
+        assert torch.allclose(a, b, atol=1e-5, rtol=1e-5)
+    assert torch.allclose(ref.get_pw_poses(), net.get_pw_poses(), atol=1e-6)
