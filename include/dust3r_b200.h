@@ -122,6 +122,39 @@ int d3r_align_pts3d(const d3r_align_desc* desc, float* out_dev, void* stream);
 int d3r_align_pack_obs(const float* pts_dev, const float* weight_dev, void* obs_dev, int64_t obs_off,
                        int64_t n_pix, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Path 1 building blocks — exported so the parity tests can exercise each kernel in isolation.
+ * Integrators use d3r_forward_* below; these are the ops it is composed of.
+ * ------------------------------------------------------------------------------------------ */
+
+/* epilogue flags of d3r_gemm_bf16 / d3r_conv3x3_bf16 */
+#define D3R_F_BIAS          (1u << 0)
+#define D3R_F_GELU          (1u << 1)   /* exact erf GELU (croco/models/blocks.py Mlp act_layer=nn.GELU) */
+#define D3R_F_RELU          (1u << 2)
+#define D3R_F_OUT_F32       (1u << 3)
+#define D3R_F_RESID_INPLACE (1u << 4)   /* out(f32) += result : residual stream update                   */
+#define D3R_F_ADD0          (1u << 5)
+#define D3R_F_ADD1          (1u << 6)
+#define D3R_F_OUT2_RELU     (1u << 7)
+#define D3R_F_ROPE          (1u << 8)   /* 2D RoPE on columns < rope_cols; replaces curope.rope_2d        */
+#define D3R_F_OUT2_BF16     (1u << 11)
+
+/* out[M,N] = epilogue(A[M,K] * B[N,K]^T); A, B bf16 row-major (nn.Linear weight layout), tcgen05.
+ * N % 32 == 0, K % 8 == 0.  With D3R_F_ROPE: rope_cos/sin are [max_pos][16] fp32 tables
+ * (angle = pos * base^(-k/16), croco/models/curope/kernels.cu:41-52), rows are tokens of images of
+ * `tokens_per_img` tokens laid out row-major on a grid `grid_w` wide. */
+int d3r_gemm_bf16(const void* A_dev, const void* B_dev, void* out_dev, const float* bias_dev, const void* add0_dev,
+                  void* out2_dev, int32_t M, int32_t N, int32_t K, int64_t ldo, uint32_t flags,
+                  const float* rope_cos_dev, const float* rope_sin_dev, int32_t rope_cols, int32_t tokens_per_img,
+                  int32_t grid_w, void* stream);
+
+/* 3x3 stride-1 pad-1 convolution as implicit GEMM on tcgen05.  x: (B,H,W,Cin) bf16 NHWC;
+ * w_packed: [Cout][ky*3+kx][Cin] bf16; out/add0/add1/out2: (B,H,W,Cout) bf16 NHWC.
+ * (croco/models/dpt_block.py ResidualConvUnit_custom / layer_rn / head convs) */
+int d3r_conv3x3_bf16(const void* x_nhwc_dev, const void* w_packed_dev, void* out_dev, const float* bias_dev,
+                     const void* add0_dev, const void* add1_dev, void* out2_dev, int32_t B, int32_t H, int32_t W,
+                     int32_t Cin, int32_t Cout, uint32_t flags, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
