@@ -155,6 +155,89 @@ int d3r_conv3x3_bf16(const void* x_nhwc_dev, const void* w_packed_dev, void* out
                      const void* add0_dev, const void* add1_dev, void* out2_dev, int32_t B, int32_t H, int32_t W,
                      int32_t Cin, int32_t Cout, uint32_t flags, void* stream);
 
+/* softmax(q k^T * scale) v, head dim 64, bf16 in/out, fp32 softmax (croco/models/blocks.py:94-112,
+ * 146-169).  q rows at (b*Nq+i)*ldq + h*64, k/v rows at (b*Nk+j)*ld{k,v} + h*64, out like q. */
+int d3r_attention_hd64(const void* q_dev, int64_t ldq, const void* k_dev, int64_t ldk, const void* v_dev, int64_t ldv,
+                       void* out_dev, int64_t ldo, int32_t B, int32_t heads, int32_t Nq, int32_t Nk, float scale,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Path 1 — pairwise forward: replaces AsymmetricCroCo3DStereo.forward (dust3r/model.py:199-211 =
+ * _encode_symmetrized :153-170, _decoder :172-191, downstream heads :193-208) for one batch of
+ * same-sized pairs.  Weights are caller-owned device buffers, repacked once by the host side
+ * (dust3r_b200/model.py: bf16 GEMM operands, fp32 biases / LayerNorm parameters).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct d3r_linear { const void* w; const float* b; } d3r_linear;  /* w: bf16 [out][in]; b may be NULL */
+typedef struct d3r_norm { const float* g; const float* b; } d3r_norm;     /* LayerNorm weight / bias (fp32)   */
+
+typedef struct d3r_enc_block {      /* croco/models/blocks.py:114-130 */
+  d3r_norm norm1, norm2;
+  d3r_linear qkv, proj, fc1, fc2;
+} d3r_enc_block;
+
+typedef struct d3r_dec_block {      /* croco/models/blocks.py:171-191 */
+  d3r_norm norm1, norm2, norm3, norm_y;
+  d3r_linear qkv, proj;             /* self attention                                             */
+  d3r_linear projq, projkv, cproj;  /* cross attention; projkv = rows of projk then projv          */
+  d3r_linear fc1, fc2;
+} d3r_dec_block;
+
+typedef struct d3r_fusion {         /* FeatureFusionBlock_custom, croco/models/dpt_block.py:130-212 */
+  d3r_linear rcu1_conv1, rcu1_conv2, rcu2_conv1, rcu2_conv2; /* 3x3, packed [Cout][9][Cin]           */
+  d3r_linear out_conv;                                     /* 1x1 [256][256]                        */
+} d3r_fusion;
+
+typedef struct d3r_dpt_head {       /* DPTOutputAdapter_fix, dust3r/heads/dpt_head.py:20-65         */
+  d3r_linear act_conv[4];           /* 1x1 convs on the 4 hooked token maps                        */
+  d3r_linear act0_up;               /* ConvTranspose k4 s4 as GEMM  [(ky*4+kx)*96+co][ci]           */
+  d3r_linear act1_up;               /* ConvTranspose k2 s2 as GEMM  [(ky*2+kx)*192+co][ci]          */
+  d3r_linear act3_down;             /* 3x3 s2 p1 as GEMM over im2col [768][9*768]                   */
+  d3r_linear layer_rn[4];           /* 3x3, no bias, packed                                        */
+  d3r_fusion refine[4];             /* refinenet1..4                                               */
+  d3r_linear head0;                 /* 3x3 256->128 packed                                         */
+  d3r_linear head2;                 /* 3x3 128->128 packed                                         */
+  const float* head4_w;             /* fp32 [nch][128]                                             */
+  const float* head4_b;             /* fp32 [nch]                                                  */
+} d3r_dpt_head;
+
+typedef struct d3r_model {
+  int32_t enc_dim, enc_depth, enc_heads, dec_dim, dec_depth, dec_heads, mlp_ratio, patch;
+  int32_t head_type;                /* 0 = linear (LinearPts3d), 1 = dpt                            */
+  int32_t nch;                      /* 3 + has_conf                                                */
+  int32_t depth_mode;               /* 0 linear, 1 square, 2 exp  (postprocess.py:23-44)            */
+  int32_t conf_mode;                /* 0 none, 1 exp, 2 sigmoid   (postprocess.py:47-58)            */
+  float conf_min, conf_max, ln_eps;
+  int32_t hooks[4];                 /* DPT hooks into [enc_out, dec_1..dec_L] (dpt_head.py:110)     */
+  int32_t rope_max_pos;
+  const float* rope_cos;            /* [rope_max_pos][16]                                          */
+  const float* rope_sin;
+  d3r_linear patch_embed;           /* [enc_dim][3*patch*patch]                                    */
+  const d3r_enc_block* enc;         /* host array [enc_depth]                                      */
+  d3r_norm enc_norm;
+  d3r_linear decoder_embed;
+  const d3r_dec_block* dec1;        /* dec_blocks   (host array [dec_depth])                       */
+  const d3r_dec_block* dec2;        /* dec_blocks2                                                 */
+  d3r_norm dec_norm;
+  const d3r_dpt_head* dpt[2];       /* downstream_head1/2 when head_type == 1                      */
+  d3r_linear lin_head[2];           /* downstream_head{1,2}.proj when head_type == 0               */
+} d3r_model;
+
+/* Bytes of device workspace d3r_forward_pairs needs for (n_enc images to encode, B pairs, HxW). */
+int64_t d3r_forward_workspace_bytes(const d3r_model* m, int32_t n_enc, int32_t B, int32_t H, int32_t W);
+
+/* imgs: (n_enc,3,H,W) fp32 in [-1,1] — the images the encoder runs on (model.py:142-170 decides which:
+ * cat(img1,img2), or only the even halves for a symmetrised batch).  idx1/idx2: HOST int32[B], the
+ * encoded image acting as view1 / view2 of pair b.  Outputs (fp32, device):
+ * pts3d_1 (B,H,W,3), conf_1 (B,H,W) in view1's frame for view1; pts3d_2 / conf_2 for view2
+ * ('pts3d_in_other_view').  conf pointers may be NULL when the model has no confidence channel. */
+int d3r_forward_pairs(const d3r_model* m, const float* imgs_dev, int32_t n_enc, const int32_t* idx1_host,
+                      const int32_t* idx2_host, int32_t B, int32_t H, int32_t W, float* pts3d_1, float* conf_1,
+                      float* pts3d_2, float* conf_2, void* workspace_dev, int64_t workspace_bytes, void* stream);
+
+/* Optional taps for the parity tests: when non-NULL, fp32 copies of intermediate stages are written.
+ * (set with d3r_forward_set_debug before a call; cleared after it).  stage ids in DESIGN.md. */
+int d3r_forward_set_debug(int32_t stage_id, float* out_dev, int64_t capacity_floats);
+
 #ifdef __cplusplus
 }
 #endif
