@@ -222,6 +222,9 @@ typedef struct d3r_model {
   d3r_linear lin_head[2];           /* downstream_head{1,2}.proj when head_type == 0               */
 } d3r_model;
 
+/* sizeof(d3r_model) as compiled into the library (binding self-check). */
+int d3r_sizeof_model(void);
+
 /* Bytes of device workspace d3r_forward_pairs needs for (n_enc images to encode, B pairs, HxW). */
 int64_t d3r_forward_workspace_bytes(const d3r_model* m, int32_t n_enc, int32_t B, int32_t H, int32_t W);
 
