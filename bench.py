@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of dust3r_b200 (contract in the task statement / DESIGN.md §Measurement).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3                       # our arm, 1 GPU
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W      # our arm, N GPUs (weak scaling)
+    python bench.py --impl reference --gpus 1 --steps K --warmup W      # reference arm: CPU path on host cores
+
+Workload (BASELINE.json configs[1]): one step = forward of a batch of 32 synthetic 512x384 pairs through
+ViT-L encoder / 2x ViT-B decoder / DPT heads ("ViTLarge_BaseDecoder_512_dpt"), random-init weights.  With
+N>1 every rank runs its own 32 pairs (configs[3]: 256 pairs over 8 GPUs) and the step ends with the single
+NCCL all-gather of the per-pair pointmaps the north_star prescribes before alignment.
+`value` is device-timed with inputs resident in HBM; `e2e` goes through the public inference() API with
+pinned HOST inputs and CPU outputs.  Extra key `cloud_opt`: BASELINE configs[2] (8 views -> 28 pairs,
+PointCloudOptimizer, 300 iterations) iterations/s with its own HBM roofline.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GFLOP_PER_PAIR = 1856.8          # SURVEY §8d / BASELINE.md §2 (2*MAC, enc 1046.1 + dec 437.3 + heads 373.4)
+H, W = 384, 512
+PAIRS_PER_GPU = 32
+METRIC = 'image-pairs/sec (512x384, ViT-L/B+DPT)'
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p['hbm_gbs'], tf_burst=p['bf16_tflops'], tf_sustained=p.get('bf16_tflops_sustained', p['bf16_tflops']),
+                    source='measured (MEASURED_PEAKS.json)')
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.stop = gpu_index, [], threading.Event()
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i', str(self.idx)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(',')])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace('.', '').isdigit()]
+        reasons = set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].lower().startswith('active'):
+                    reasons.add(nm)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(self.rows))
+
+
+def build_model(device):
+    from dust3r_b200.config import vitl_512_dpt
+    from dust3r_b200.model import AsymmetricCroCo3DStereo
+    from dust3r_b200.utils.synth import synth_state_dict
+    cfg = vitl_512_dpt()
+    net = AsymmetricCroCo3DStereo(pos_embed='RoPE100', img_size=(512, 512), head_type='dpt', output_mode='pts3d',
+                                  depth_mode=('exp', -float('inf'), float('inf')), conf_mode=('exp', 1, float('inf')),
+                                  enc_embed_dim=1024, enc_depth=24, enc_num_heads=16, dec_embed_dim=768, dec_depth=12,
+                                  dec_num_heads=12, landscape_only=False)
+    net.load_state_dict(synth_state_dict(cfg, seed=0))
+    return net.to(device), cfg
+
+
+def synth_pairs_host(n_pairs, seed, pin):
+    """n_pairs distinct pairs (2*n_pairs images) in load_images' format, pinned host memory."""
+    g = torch.Generator().manual_seed(seed)
+    views = []
+    for i in range(2 * n_pairs):
+        img = torch.rand((1, 3, H, W), generator=g) * 2 - 1
+        if pin:
+            img = img.pin_memory()
+        views.append(dict(img=img, true_shape=np.int32([[H, W]]), idx=i, instance=str(i)))
+    return [(views[2 * k], views[2 * k + 1]) for k in range(n_pairs)]
+
+
+def cloud_opt_section(device, pk, steps_iters=300):
+    """BASELINE configs[2]: 8 views -> 28 pairs (symmetrize=False), PointCloudOptimizer, 300 iterations."""
+    from dust3r_b200.utils.synth import synth_pair_predictions
+    from dust3r_b200.cloud_opt import global_aligner
+    n = 8
+    edges = [(i, j) for i in range(n) for j in range(i)]
+    out = synth_pair_predictions(n, edges, H, W, seed=0)
+    torch.manual_seed(0)
+    net = global_aligner(out, device, verbose=False)
+    eng = net._get_engine()
+    net._engine_push(eng)
+    eng.run(30)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    losses = eng.run(steps_iters)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    by = eng.algorithmic_bytes_per_iter()
+    gbs = by / (ms / steps_iters) / 1e6
+    # e2e through the public API: host dict in -> global_aligner -> compute_global_alignment -> float loss
+    t0 = time.perf_counter()
+    torch.manual_seed(0)
+    net2 = global_aligner(out, device, verbose=False)
+    loss = net2.compute_global_alignment(init=None, niter=steps_iters, schedule='cosine', lr=0.01)
+    torch.cuda.synchronize()
+    t_api = time.perf_counter() - t0
+    return dict(metric='cloud_opt iters/sec', value=steps_iters / ms * 1e3, unit='iters/s',
+                config=dict(workload='8 synthetic views -> 28 pairs (symmetrize=False) at 512x384, PointCloudOptimizer, '
+                                     '300 iters, lr 0.01 cosine, dist l1, conf log, init=None'),
+                ms_per_iter=ms / steps_iters, loss_first=float(losses[0]), loss_last=float(losses[-1]),
+                roofline=dict(bound='hbm', achieved=gbs, peak=pk['hbm'], unit='GB/s', frac=gbs / pk['hbm'], traffic=None,
+                              algorithmic_bytes_per_iter=by, peak_source=pk['source']),
+                e2e=dict(value=steps_iters / t_api, unit='iters/s', includes='H2D of 28 pairs of predictions, packing, 300 iters, loss readback',
+                         final_loss=loss))
+
+
+def cpu_baseline_forward(n_pairs=1):
+    """Oracle port (CPU fp32 torch restatement of the reference forward) on the host cores."""
+    from dust3r_b200.config import vitl_512_dpt
+    from dust3r_b200.utils.synth import synth_state_dict, synth_images
+    from oracle.forward_oracle import forward_oracle
+    cfg = vitl_512_dpt()
+    sd = synth_state_dict(cfg, seed=0)
+    imgs = synth_images(2, H, W, seed=3)
+    forward_oracle(sd, cfg, imgs[0]['img'][:, :, :64, :64], imgs[1]['img'][:, :, :64, :64])  # warm the thread pool
+    t0 = time.perf_counter()
+    for _ in range(n_pairs):
+        forward_oracle(sd, cfg, imgs[0]['img'], imgs[1]['img'])
+    dt = time.perf_counter() - t0
+    return dict(value=n_pairs / dt, unit='image-pairs/s', cores=torch.get_num_threads(), kind='port',
+                sample=f'{n_pairs} pair(s) of 512x384, batch 1, oracle/forward_oracle.py (fp32 torch CPU restatement of the reference)')
+
+
+def run_reference_arm(args):
+    """Reference arm: the reference's own CPU implementation of the path.  /root/reference does not exist on
+    the GPU box and the reference has no compiled component for this path, so this times the oracle port
+    (validated bit-for-bit against the live reference in tests/test_oracle.py) on all host cores."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from dust3r_b200.config import vitl_512_dpt
+    from dust3r_b200.utils.synth import synth_state_dict, synth_images
+    from oracle.forward_oracle import forward_oracle
+    cfg = vitl_512_dpt()
+    sd = synth_state_dict(cfg, seed=0)
+    imgs = synth_images(2, H, W, seed=3)
+    sample_pairs = 1
+    for _ in range(max(args.warmup, 1) if args.warmup else 0):
+        forward_oracle(sd, cfg, imgs[0]['img'], imgs[1]['img'])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for _ in range(sample_pairs):
+            forward_oracle(sd, cfg, imgs[0]['img'], imgs[1]['img'])
+    dt = time.perf_counter() - t0
+    val = args.steps * sample_pairs / dt
+    cores = torch.get_num_threads()
+    line = dict(impl='reference', metric=METRIC, value=val, unit='image-pairs/s', n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=dt / args.steps * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype='f32', data='synthetic',
+                config=dict(workload='32 synthetic 512x384 pairs, ViTLarge_BaseDecoder_512_dpt forward (bounded sample: '
+                                     f'{sample_pairs} pair per step)', device='cpu'),
+                cpu_baseline=dict(value=val, unit='image-pairs/s', cores=cores, kind='port',
+                                  sample=f'{sample_pairs} pair per step x {args.steps} steps, batch 1'),
+                e2e=dict(value=val, unit='image-pairs/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--pairs', type=int, default=PAIRS_PER_GPU, help='pairs per GPU per step')
+    ap.add_argument('--skip-cpu-baseline', action='store_true')
+    ap.add_argument('--skip-cloud-opt', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == 'reference':
+        return run_reference_arm(args)
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py (our arm) needs a CUDA B200; there is no CPU fallback')
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+    from dust3r_b200 import _lib
+    from dust3r_b200.inference import inference
+    pk = peaks()
+    B = args.pairs
+    net, cfg = build_model(device)
+    packed = net.repack()
+    g = torch.Generator(device='cpu').manual_seed(1234 + rank)
+    imgs = (torch.rand((2 * B, 3, H, W), generator=g) * 2 - 1).to(device)
+    idx1, idx2 = np.arange(B, dtype=np.int32), B + np.arange(B, dtype=np.int32)
+    gather_bufs = None
+
+    def step():
+        r1, r2 = packed.forward(imgs, idx1, idx2, B, H, W)
+        if world > 1:
+            # the one collective of the path: all-gather of {pts3d, conf} x 2 (6.29 MB / pair)
+            nonlocal gather_bufs
+            flat = torch.cat((r1['pts3d'].reshape(B, -1), r1['conf'].reshape(B, -1), r2['pts3d'].reshape(B, -1), r2['conf'].reshape(B, -1)), dim=1)
+            if gather_bufs is None:
+                gather_bufs = torch.empty((world,) + tuple(flat.shape), dtype=flat.dtype, device=device)
+            dist.all_gather_into_tensor(gather_bufs, flat)
+        return r1, r2
+
+    W_ = max(args.warmup, 3)
+    for _ in range(W_):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    _lib.launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+    launches = _lib.launch_count()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms[0])
+    value = world * B * args.steps / ms_total * 1e3
+
+    # ---- per-kernel-class breakdown (one extra instrumented step; not part of the timed region) ----
+    _lib.prof_enable(True)
+    step()
+    torch.cuda.synchronize()
+    prof = _lib.prof_report()
+    _lib.prof_enable(False)
+    kern = {}
+    tot_ms = sum(v['ms'] for v in prof.values()) or 1.0
+    for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms']):
+        kern[k] = dict(launches=v['count'], ms=round(v['ms'], 3), share=round(v['ms'] / tot_ms, 4),
+                       tflops=round(v['flops'] / v['ms'] / 1e9, 1) if v['flops'] and v['ms'] else None,
+                       gbs=round(v['bytes'] / v['ms'] / 1e6, 1) if v['bytes'] and v['ms'] else None)
+    dom = max(prof.items(), key=lambda kv: kv[1]['ms'])
+    dom_tflops = dom[1]['flops'] / dom[1]['ms'] / 1e9 if dom[1]['flops'] else 0.0
+
+    # ---- e2e through the public API: pinned host pairs -> inference() -> CPU dict ----
+    e2e = None
+    if rank == 0 or world > 1:
+        pairs = synth_pairs_host(B, seed=99 + rank, pin=True)
+        inference(pairs, net, device, batch_size=B, verbose=False)  # warm-up
+        torch.cuda.synchronize()
+        n_e2e = max(2, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            out = inference(pairs, net, device, batch_size=B, verbose=False)
+            _ = float(out['pred1']['conf'][0, 0, 0])
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=device)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        h2d = 2 * B * 3 * H * W * 4
+        d2h = 2 * B * H * W * 4 * 4 + 2 * B * 3 * H * W * 4   # predictions + the views inference() returns (to_cpu(res))
+        e2e = dict(value=world * B * n_e2e / float(dt[0]), unit='image-pairs/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                   api='dust3r_b200.inference.inference(pairs, model, device, batch_size=32)')
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    clocks = clk.summary()
+    alg_tflops = value * GFLOP_PER_PAIR / 1e3
+    peak = pk['tf_sustained'] * world
+    line = dict(metric=METRIC, value=value, unit='image-pairs/s', n_gpus=world, steps=args.steps, warmup=W_,
+                ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16',
+                data='synthetic',
+                config=dict(workload=f'{B} synthetic 512x384 pairs per GPU per step ({world * B} total), '
+                                     'ViTLarge_BaseDecoder_512_dpt forward only, not symmetrised (encoder sees 2 images/pair)'
+                                     + (', + NCCL all-gather of pointmaps' if world > 1 else ''),
+                            weights='random init (synthetic, seed 0)', compute='bf16 operands / fp32 accumulate / fp32 residual stream',
+                            l2='activations per step (>5 GB) exceed the 126 MB L2; no explicit flush needed',
+                            parallelism=f'dp{world}'),
+                clocks=clocks, e2e=e2e, gpu_launches=int(launches),
+                roofline=dict(bound='tensor', achieved=alg_tflops, peak=peak, unit='TFLOP/s', frac=alg_tflops / peak, traffic=None,
+                              what='whole step: pairs/s x 1856.8 GFLOP/pair (SURVEY §8d) vs measured cuBLAS bf16 sustained peak',
+                              peak_source=pk['source'],
+                              dominant_kernel=dict(name=dom[0], tflops=dom_tflops, frac_of_burst_peak=dom_tflops / pk['tf_burst'],
+                                                   share_of_step=dom[1]['ms'] / tot_ms)),
+                kernels=kern)
+    if world == 1 and not args.skip_cpu_baseline:
+        line['cpu_baseline'] = cpu_baseline_forward(1)
+    if world == 1 and not args.skip_cloud_opt:
+        del packed, net, imgs
+        torch.cuda.empty_cache()
+        line['cloud_opt'] = cloud_opt_section(device, pk)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

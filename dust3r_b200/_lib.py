@@ -43,6 +43,12 @@ def _declare(lib):
     lib.d3r_abi_version.restype = C.c_int
     lib.d3r_check_device.restype = C.c_int
     lib.d3r_align_chunk_pixels.restype = C.c_int
+    lib.d3r_launch_count.restype = C.c_longlong
+    lib.d3r_launch_count_reset.restype = None
+    lib.d3r_prof_enable.restype = None
+    lib.d3r_prof_enable.argtypes = [C.c_int]
+    lib.d3r_prof_report.restype = C.c_int
+    lib.d3r_prof_report.argtypes = [C.c_char_p, C.c_int]
     lib.d3r_sizeof_align_desc.restype = C.c_int
     lib.d3r_align_workspace_floats.restype = i64
     lib.d3r_align_workspace_floats.argtypes = [i32, i32, i32, i32]
@@ -98,3 +104,24 @@ def require_cuda_device(device):
 def stream_ptr():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count(reset=False):
+    lib = get_lib()
+    n = int(lib.d3r_launch_count())
+    if reset:
+        lib.d3r_launch_count_reset()
+    return n
+
+
+def prof_enable(on=True):
+    get_lib().d3r_prof_enable(1 if on else 0)
+
+
+def prof_report():
+    import json
+    buf = C.create_string_buffer(1 << 16)
+    n = get_lib().d3r_prof_report(buf, len(buf))
+    if n < 0:
+        raise D3RError('profile report does not fit the buffer')
+    return json.loads(buf.value.decode())

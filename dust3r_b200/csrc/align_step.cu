@@ -18,6 +18,7 @@
 //          signed_expm1 and the mean-coupled scale backward done analytically), applies Adam and
 //          writes the transforms of the next iteration.
 #include "d3r_common.cuh"
+#include "prof.h"
 
 namespace d3r {
 namespace align {
@@ -595,6 +596,7 @@ extern "C" int d3r_align_run(const d3r_align_desc* desc, int32_t it_begin, int32
   } else {
     D3R_CUDA(cudaFuncSetAttribute(align_iter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
+  prof::Scope scope("align_iter", (cudaStream_t)stream, 0.0, 0.0, it_end - it_begin);
   for (int it = it_begin; it < it_end; ++it) {
     if (desc->dist_l2)
       align_iter_kernel<true><<<desc->n_chunks, kThreads, smem, (cudaStream_t)stream>>>(*desc, it);

@@ -8,6 +8,7 @@
 // pins the numerics and the interface.
 #include "d3r_common.cuh"
 #include "elementwise.h"
+#include "prof.h"
 #include <cuda_bf16.h>
 
 namespace d3r {
@@ -184,6 +185,7 @@ int attention_hd64(const void* q, long long ldq, const void* k, long long ldk, c
   D3R_CHECK_ARG(q && k && v && out && B > 0 && heads > 0 && Nq > 0 && Nk > 0, "attention: bad arguments");
   D3R_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 2 == 0, "attention: row strides must keep 16-byte alignment");
   dim3 grid((Nq + BM - 1) / BM, heads, B);
+  prof::Scope scope("attention_hd64", st, 4.0 * double(B) * heads * double(Nq) * double(Nk) * 64.0);
   attention_kernel<<<grid, kThreads, 0, st>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk, (const __nv_bfloat16*)v, ldv,
                                                (__nv_bfloat16*)out, ldo, Nq, Nk, scale * 1.4426950408889634f);
   D3R_LAUNCH_CHECK();

@@ -4,6 +4,7 @@
 // postprocess.  All coalesced, 16-byte vectorised where the layout allows.
 #include "d3r_common.cuh"
 #include "elementwise.h"
+#include "prof.h"
 #include <cuda_bf16.h>
 
 namespace d3r {
@@ -68,6 +69,7 @@ int layernorm(const float* x, const float* g, const float* b, void* out_bf16, co
   D3R_CHECK_ARG(C % 4 == 0 && C <= 2048, "layernorm: C=%d unsupported", C);
   const int warps = 8;
   const int blocks = (M + warps - 1) / warps;
+  prof::Scope scope("layernorm", st, 0.0, double(M) * C * 6.0);
   if (C <= 1024)
     layernorm_kernel<8><<<blocks, warps * 32, 0, st>>>(x, g, b, (__nv_bfloat16*)out_bf16, row_map, M, C, eps);
   else
@@ -88,6 +90,7 @@ int cast_f32_bf16(const float* x, void* out, size_t n, cudaStream_t st) {
   D3R_CHECK_ARG(n % 4 == 0, "cast: n must be a multiple of 4");
   const size_t n4 = n / 4;
   if (n4 == 0) return D3R_OK;
+  prof::Scope scope("cast_f32_bf16", st, 0.0, double(n) * 6.0);
   cast_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>((const float4*)x, (uint2*)out, n4);
   D3R_LAUNCH_CHECK();
   return D3R_OK;
@@ -109,6 +112,7 @@ int gather_images_bf16(const void* in, void* out, const int* img_map_dev, int n_
   const int vpr = C / 8;
   const size_t total = (size_t)n_out_imgs * rows_per_img * vpr;
   if (!total) return D3R_OK;
+  prof::Scope scope("gather_images", st, 0.0, double(total) * 32.0);
   gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const uint4*)in, (uint4*)out, img_map_dev, rows_per_img, vpr, total);
   D3R_LAUNCH_CHECK();
   return D3R_OK;
@@ -136,6 +140,7 @@ __global__ void patch_im2col_kernel(const float* __restrict__ img, __nv_bfloat16
 int patch_im2col16(const float* img, void* out, int B, int H, int W, cudaStream_t st) {
   D3R_CHECK_ARG(H % 16 == 0 && W % 16 == 0, "patch_im2col: image %dx%d is not a multiple of the 16-pixel patch", H, W);
   const size_t total = (size_t)B * (H / 16) * (W / 16) * 48;
+  prof::Scope scope("patch_im2col", st, 0.0, double(total) * 96.0);
   patch_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(img, (__nv_bfloat16*)out, B, H, W, H / 16, W / 16);
   D3R_LAUNCH_CHECK();
   return D3R_OK;
@@ -183,6 +188,7 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bflo
 int upsample2x_bf16(const void* x, void* out, int B, int H, int W, int C, int Ho, int Wo, cudaStream_t st) {
   D3R_CHECK_ARG(C % 8 == 0 && Ho <= 2 * H && Wo <= 2 * W, "upsample2x: bad shape");
   const size_t total = (size_t)B * Ho * Wo * (C / 8);
+  prof::Scope scope("upsample2x", st, 0.0, double(total) * 20.0);
   upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, B, H, W, C, Ho, Wo);
   D3R_LAUNCH_CHECK();
   return D3R_OK;
@@ -212,6 +218,7 @@ int im2col_3x3_s2_bf16(const void* x, void* out, int B, int H, int W, int C, cud
   D3R_CHECK_ARG(C % 8 == 0, "im2col_s2: C must be a multiple of 8");
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const size_t total = (size_t)B * Ho * Wo * 9 * (C / 8);
+  prof::Scope scope("im2col_s2", st, 0.0, double(total) * 32.0);
   im2col_s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, B, H, W, C, Ho, Wo);
   D3R_LAUNCH_CHECK();
   return D3R_OK;
@@ -251,6 +258,7 @@ __global__ void linear_head_post_kernel(const float* __restrict__ feat, float* _
 int linear_head_postprocess(const float* feat, float* pts3d, float* conf, int B, int gh, int gw, int nch, int depth_mode,
                             int conf_mode, float cmin, float cmax, cudaStream_t st) {
   const size_t total = (size_t)B * gh * gw * 256;
+  prof::Scope scope("linear_head_post", st, 0.0, double(total) * 32.0);
   linear_head_post_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(feat, pts3d, conf, B, gh, gw, nch, depth_mode, conf_mode, cmin, cmax);
   D3R_LAUNCH_CHECK();
   return D3R_OK;

@@ -1,6 +1,7 @@
 // Host side of the tcgen05 GEMM / conv kernels: tensor-map construction, tile-shape selection, launch.
 #include "gemm_tcgen05.cuh"
 #include "gemm_host.h"
+#include "prof.h"
 #include <mutex>
 
 namespace d3r {
@@ -58,6 +59,9 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
     attr_set = true;
   }
   int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  const char* tag = (p.mode == 1) ? ((p.flags & F_HEAD_FINAL) ? "conv3x3_head_tail" : "conv3x3_tcgen05")
+                                  : (BN == 256 ? "gemm_tcgen05_bn256" : (BN == 128 ? "gemm_tcgen05_bn128" : "gemm_tcgen05_bn64"));
+  prof::Scope scope(tag, st, 2.0 * double(p.M) * double(p.N) * double(p.K));
   gemm_kernel<BN><<<grid, kNumThreads, Cfg<BN>::kSmemBytes, st>>>(ta, tb, p);
   D3R_LAUNCH_CHECK();
   return D3R_OK;

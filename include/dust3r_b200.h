@@ -36,6 +36,15 @@ int d3r_abi_version(void);
 /* 0 when the current device is sm_100 (B200); D3R_ERR_UNSUPPORTED_DEVICE otherwise. */
 int d3r_check_device(void);
 
+/* Launch accounting / profiling aid: number of kernels this library launched since the last reset;
+ * with d3r_prof_enable(1) every launch is bracketed by CUDA events on its stream and
+ * d3r_prof_report() returns a JSON object {tag: {count, ms, flops, bytes}} (returns length, -1 if
+ * the buffer is too small). */
+long long d3r_launch_count(void);
+void d3r_launch_count_reset(void);
+void d3r_prof_enable(int on);
+int d3r_prof_report(char* buf, int cap);
+
 /* ------------------------------------------------------------------------------------------
  * Path 2 — global alignment (replaces the body of global_alignment_iter(),
  * dust3r/cloud_opt/base_opt.py:352-366: zero_grad + PointCloudOptimizer.forward
