@@ -66,7 +66,7 @@ def build(force=False, verbose=False):
         objs = list(ex.map(lambda s: _compile(s, log), sources()))
     newest = max(os.path.getmtime(o) for o in objs)
     if force or not os.path.exists(OUT) or os.path.getmtime(OUT) < newest:
-        cmd = [NVCC] + ARCH + ['-shared', '-o', OUT] + objs + ['-lcuda']
+        cmd = [NVCC] + ARCH + ['-shared', '-o', OUT] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f'link failed:\n{r.stdout}\n{r.stderr}')

@@ -2,12 +2,12 @@
 //
 //   D[M,N] = A[M,K] * B[N,K]^T   (both operands K-major, fp32 accumulation in TMEM)
 //
-// Roles (192 threads, 1 CTA / SM, grid = min(#tiles, #SMs), static round-robin tile schedule with the
+// Roles (320 threads, 1 CTA / SM, grid = min(#tiles, #SMs), static round-robin tile schedule with the
 // N index fastest so the CTAs of one wave share A rows through L2):
 //   warp 0      TMA producer   : cp.async.bulk.tensor -> 128B-swizzled smem ring (kStages deep)
 //   warp 1      MMA issuer     : one elected lane issues tcgen05.mma (UMMA 128 x BLOCK_N x 16),
 //                                tcgen05.commit releases smem slots / publishes the accumulator
-//   warps 2..5  epilogue       : tcgen05.ld (32 lanes x 32 columns per instruction) -> fused epilogue
+//   warps 2..9  epilogue       : tcgen05.ld (32 lanes x 32 columns per instruction) -> fused epilogue
 //                                -> global.  Two TMEM accumulator buffers overlap epilogue(i) with
 //                                the mainloop of tile i+1.
 //
@@ -28,7 +28,8 @@ namespace gemm {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle atom row
 constexpr int UMMA_K = 16;
-constexpr int kNumThreads = 192;
+constexpr int kNumEpilogueWarps = 8;  // two warps per TMEM lane quarter, each draining half of the columns
+constexpr int kNumThreads = 64 + 32 * kNumEpilogueWarps;
 
 enum : uint32_t {
   F_BIAS = 1u << 0,
@@ -84,7 +85,18 @@ struct Cfg {
   static constexpr int kSmemBytes = kStages * (kStageA + kStageB) + 1024 /*align*/ + 256 /*barriers*/ + 4 * 128 * 4 + 64;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// exact-erf GELU (nn.GELU default).  erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the
+// bf16 rounding of the stored activation); ~3x fewer instructions than erff() in the epilogue hot loop.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = 1.f - poly * t * __expf(-z * z);   // erf(|x|/sqrt2)
+  return 0.5f * x * (1.f + copysignf(e, x));
+}
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -124,7 +136,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(ptx::smem_u32(&tfull_bar[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&tempty_bar[s]), 4);
+      ptx::mbar_init(ptx::smem_u32(&tempty_bar[s]), kNumEpilogueWarps);
     }
     ptx::fence_barrier_init();
   }
@@ -134,7 +146,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     ptx::tmem_relinquish();
   }
   if ((p.flags & F_HEAD_FINAL) && threadIdx.x >= 64) {
-    for (int i = threadIdx.x - 64; i < 4 * 128 + 4; i += 128) s_w4[i] = (i < 512) ? p.w4[i] : p.b4[i - 512];
+    for (int i = threadIdx.x - 64; i < 4 * 128 + 4; i += 32 * kNumEpilogueWarps) s_w4[i] = (i < 512) ? p.w4[i] : p.b4[i - 512];
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -207,6 +219,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     // ================= epilogue warps =================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int row_in_tile = quarter * 32 + lane;
+    // column split between the two warps of a quarter; the head tail needs whole rows -> first warp only
+    constexpr int kChunks = BLOCK_N / 32;
+    const int half = (warp - 2) >> 2;
+    const bool whole_row = (p.flags & F_HEAD_FINAL) != 0;
+    const int ch_begin = whole_row ? 0 : half * (kChunks / 2);
+    const int ch_end = whole_row ? (half == 0 ? kChunks : 0) : (half + 1) * (kChunks / 2);
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t flags = p.flags;
@@ -243,7 +261,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       ptx::mbar_wait(ptx::smem_u32(&tfull_bar[acc]), acc_phase);
       ptx::tc_fence_after();
 #pragma unroll 1
-      for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+      for (int ch = ch_begin; ch < ch_end; ++ch) {
         const int col0 = tn * BLOCK_N + ch * 32;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t raw[32];
@@ -377,7 +395,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[acc]));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
 
-      if ((flags & F_HEAD_FINAL) && valid) {
+      if ((flags & F_HEAD_FINAL) && valid && half == 0) {
         // dust3r/heads/postprocess.py: pts3d = xyz/|xyz| * f(|xyz|), conf = vmin + exp(x) (clipped)
         const float x = head_acc[0] + s_w4[512 + 0], y = head_acc[1] + s_w4[512 + 1], z = head_acc[2] + s_w4[512 + 2];
         float ox = x, oy = y, oz = z;
