@@ -300,7 +300,7 @@ def main():
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         h2d = 2 * B * 3 * H * W * 4
-        d2h = 2 * B * H * W * 4 * 4 + 2 * B * 3 * H * W * 4   # predictions + the views inference() returns (to_cpu(res))
+        d2h = 2 * B * H * W * 4 * 4   # pts3d (3 f32) + conf (1 f32) for both views; the returned views are the host originals
         e2e = dict(value=world * B * n_e2e / float(dt[0]), unit='image-pairs/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                    api='dust3r_b200.inference.inference(pairs, model, device, batch_size=32)')
 

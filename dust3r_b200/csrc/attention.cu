@@ -180,8 +180,12 @@ __global__ void __launch_bounds__(kThreads) attention_kernel(const __nv_bfloat16
   }
 }
 
+static int g_impl = 0;  // 0: mma.sync streaming kernel, 1: tcgen05/TMEM kernel (attention_tc.cu)
+void set_impl(int impl) { g_impl = impl; }
+
 int attention_hd64(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
                    long long ldo, int B, int heads, int Nq, int Nk, float scale, cudaStream_t st) {
+  if (g_impl == 1) return attention_hd64_tc(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, scale, st);
   D3R_CHECK_ARG(q && k && v && out && B > 0 && heads > 0 && Nq > 0 && Nk > 0, "attention: bad arguments");
   D3R_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 2 == 0, "attention: row strides must keep 16-byte alignment");
   dim3 grid((Nq + BM - 1) / BM, heads, B);
@@ -194,6 +198,8 @@ int attention_hd64(const void* q, long long ldq, const void* k, long long ldk, c
 
 }  // namespace attn
 }  // namespace d3r
+
+extern "C" void d3r_set_attention_impl(int32_t impl) { d3r::attn::set_impl(impl); }
 
 extern "C" int d3r_attention_hd64(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
                                   int64_t ldo, int32_t B, int32_t heads, int32_t Nq, int32_t Nk, float scale, void* stream) {

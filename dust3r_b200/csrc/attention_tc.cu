@@ -1,0 +1,350 @@
+// tcgen05 / TMEM fused attention for head dim 64 (sm_100a).
+//
+//   O = softmax(Q K^T * scale) V      per (image b, head h), bf16 in/out, fp32 softmax + accumulation
+//
+// CTA = (b, h, 128-query tile), 192 threads, 2 CTAs co-resident per SM (112 KB smem, 256 TMEM columns each)
+// so one CTA's softmax (MUFU/FMA bound) overlaps the other's tensor-core work:
+//   warp 0      TMA producer : Q tile once, then K_j / V_j (128 keys x 64) into 2-deep 128B-swizzled rings
+//   warp 1      MMA issuer   : S = Q K_j^T  (UMMA 128x128x16 x4, K-major A and B)  -> TMEM cols [0,128)
+//                              O += P V_j   (UMMA 128x64x16 x8, A = P from smem, B = V_j MN-major) -> cols [128,192)
+//   warps 2..5  softmax      : thread = query row.  tcgen05.ld S -> running max / exp2 / row sum -> P (bf16)
+//                              written to smem in the canonical K-major SW128 layout; rescales O in TMEM
+//                              (tcgen05.ld/st) when the running max moves; final 1/l normalisation + store.
+// Keys beyond Nk are masked to -inf (TMA zero-fills rows past the image because the tensor maps are 3-D
+// {cols, tokens, images}).
+#include "d3r_common.cuh"
+#include "sm100_ptx.cuh"
+#include "elementwise.h"
+#include "prof.h"
+#include <mutex>
+
+namespace d3r {
+namespace attn {
+
+namespace tc {
+
+constexpr int BQ = 128, BK = 128, D = 64;
+constexpr int kThreads = 192;
+constexpr int kTileBytes = 128 * 64 * 2;  // 16 KB: 128 rows x 128 B
+constexpr int kSmemBytes = 1024 /*align*/ + kTileBytes /*Q*/ + 2 * kTileBytes /*K ring*/ + 2 * kTileBytes /*V ring*/ +
+                           2 * kTileBytes /*P: two 64-key atoms*/ + 256 /*barriers*/;
+constexpr int kTmemCols = 256;
+constexpr uint32_t kColS = 0, kColO = 128;
+
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+      "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+      "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// MN-major (N contiguous) 128B-swizzled B operand: rows of the smem tile are K (keys), 128 B each = 64 N values.
+// 8-key groups are 1024 B apart (stride byte offset); one 64-wide N atom only, so the leading offset is unused.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr & 0x3FFFF) >> 4);
+  d |= uint64_t(1024 >> 4) << 16;
+  d |= uint64_t(1024 >> 4) << 32;
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(2) << 61;
+  return d;
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                    const __grid_constant__ CUtensorMap tmap_v, __nv_bfloat16* __restrict__ out, long long ldo, int Nq, int Nk,
+                    int q_col0, int k_col0, int v_col0, float scale_log2) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_q = smem;
+  uint8_t* s_k = s_q + kTileBytes;
+  uint8_t* s_v = s_k + 2 * kTileBytes;
+  uint8_t* s_p = s_v + 2 * kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 2 * kTileBytes);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;   // [2]
+  uint64_t* s_ready = bars + 9;   // S_j in TMEM
+  uint64_t* s_free = bars + 10;   // softmax finished reading S_j
+  uint64_t* p_ready = bars + 11;  // P_j in smem (+ O rescaled)
+  uint64_t* o_done = bars + 12;   // P V_j accumulated
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+  const int nblk = (Nk + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_q);
+    ptx::prefetch_tmap(&tmap_k);
+    ptx::prefetch_tmap(&tmap_v);
+  }
+  if (warp == 1 && lane == 0) {
+    ptx::mbar_init(ptx::smem_u32(q_full), 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&k_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&k_empty[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&v_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&v_empty[s]), 1);
+    }
+    ptx::mbar_init(ptx::smem_u32(s_ready), 1);
+    ptx::mbar_init(ptx::smem_u32(s_free), 4);
+    ptx::mbar_init(ptx::smem_u32(p_ready), 4);
+    ptx::mbar_init(ptx::smem_u32(o_done), 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    __syncwarp();
+    ptx::tmem_alloc(ptx::smem_u32(tmem_slot), kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (ptx::elect_one()) {
+      ptx::mbar_arrive_expect_tx(ptx::smem_u32(q_full), kTileBytes);
+      ptx::tma_load_3d(ptx::smem_u32(s_q), &tmap_q, ptx::smem_u32(q_full), q_col0 + h * D, q0, b);
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        ptx::mbar_wait(ptx::smem_u32(&k_empty[st]), ph ^ 1);
+        ptx::mbar_arrive_expect_tx(ptx::smem_u32(&k_full[st]), kTileBytes);
+        ptx::tma_load_3d(ptx::smem_u32(s_k + st * kTileBytes), &tmap_k, ptx::smem_u32(&k_full[st]), k_col0 + h * D, j * BK, b);
+        ptx::mbar_wait(ptx::smem_u32(&v_empty[st]), ph ^ 1);
+        ptx::mbar_arrive_expect_tx(ptx::smem_u32(&v_full[st]), kTileBytes);
+        ptx::tma_load_3d(ptx::smem_u32(s_v + st * kTileBytes), &tmap_v, ptx::smem_u32(&v_full[st]), v_col0 + h * D, j * BK, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_o = ptx::umma_idesc_bf16(128, 64, 0, 1);  // B (=V) is MN-major
+      const uint32_t d_s = tmem_base + kColS, d_o = tmem_base + kColO;
+      const uint64_t dq = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(s_q));
+      auto issue_s = [&](int j) {
+        const int st = j & 1;
+        ptx::mbar_wait(ptx::smem_u32(&k_full[st]), (j >> 1) & 1);
+        if (j > 0) ptx::mbar_wait(ptx::smem_u32(s_free), (j - 1) & 1);  // softmax has drained S_{j-1}
+        ptx::tc_fence_after();
+        const uint64_t dk = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(s_k + st * kTileBytes));
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) ptx::umma_bf16_ss(d_s, dq + uint64_t(2 * k), dk + uint64_t(2 * k), idesc_s, k ? 1u : 0u);
+        ptx::umma_commit(ptx::smem_u32(&k_empty[st]));
+        ptx::umma_commit(ptx::smem_u32(s_ready));
+      };
+      ptx::mbar_wait(ptx::smem_u32(q_full), 0);
+      issue_s(0);
+      for (int j = 0; j < nblk; ++j) {
+        if (j + 1 < nblk) issue_s(j + 1);
+        const int st = j & 1;
+        ptx::mbar_wait(ptx::smem_u32(p_ready), j & 1);
+        ptx::mbar_wait(ptx::smem_u32(&v_full[st]), (j >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t pv = ptx::smem_u32(s_v + st * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t dp = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(s_p) + (k >> 2) * kTileBytes) + uint64_t(2 * (k & 3));
+          const uint64_t dv = umma_desc_mnmajor_sw128(pv + k * 16 * 128);
+          ptx::umma_bf16_ss(d_o, dp, dv, idesc_o, (j | k) ? 1u : 0u);
+        }
+        ptx::umma_commit(ptx::smem_u32(&v_empty[st]));
+        ptx::umma_commit(ptx::smem_u32(o_done));
+      }
+    }
+  } else {
+    // ================= softmax / correction / epilogue warps =================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_addr + kColS, t_o = tmem_base + lane_addr + kColO;
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      const int nvalid = min(BK, Nk - j * BK);
+      ptx::mbar_wait(ptx::smem_u32(s_ready), j & 1);
+      ptx::tc_fence_after();
+      // pass 1: row max
+      float mx = m;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        if (c * 32 >= nvalid) break;
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(t_s + c * 32, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float v = (c * 32 + i < nvalid) ? __uint_as_float(r[i]) : -INFINITY;
+          mx = fmaxf(mx, v);
+        }
+      }
+      const float corr = exp2f((m - mx) * scale_log2);  // 0 on the first block (m = -inf)
+      const float ms = mx * scale_log2;
+      m = mx;
+      // the previous P V must have consumed P (smem) and updated O before we touch either
+      if (j > 0) {
+        ptx::mbar_wait(ptx::smem_u32(o_done), (j - 1) & 1);
+        ptx::tc_fence_after();
+      }
+      // pass 2: p = exp2(s*c - m*c), row sum, bf16 pack, swizzled store (K-major SW128: 16-B chunk ^ (row & 7))
+      float rs = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t packed[16];
+        if (c * 32 < nvalid) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(t_s + c * 32, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = (c * 32 + i < nvalid) ? fast_exp2(__uint_as_float(r[i]) * scale_log2 - ms) : 0.f;
+            const float p1 = (c * 32 + i + 1 < nvalid) ? fast_exp2(__uint_as_float(r[i + 1]) * scale_log2 - ms) : 0.f;
+            rs += p0 + p1;
+            packed[i >> 1] = pack2(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) packed[i] = 0u;
+        }
+        uint8_t* atom = s_p + (c >> 1) * kTileBytes + row * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = (c & 1) * 4 + q;
+          *reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) =
+              make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        }
+      }
+      // S_j fully read -> the MMA warp may overwrite it with S_{j+1}
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(s_free));
+      l = l * corr + rs;
+      // rescale the running output
+      if (j > 0) {
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(t_o + c * 32, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
+          tmem_st_32x32b_x32(t_o + c * 32, r);
+        }
+        tmem_st_wait();
+      }
+      // make the generic-proxy smem writes of P visible to the tensor core (async proxy), then publish
+      ptx::fence_proxy_async();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(p_ready));
+    }
+    // ---- epilogue: O / l -> bf16 -> global ----
+    ptx::mbar_wait(ptx::smem_u32(o_done), (nblk - 1) & 1);
+    ptx::tc_fence_after();
+    const float inv = 1.f / l;
+    const int qrow = q0 + row;
+    __nv_bfloat16* orow = out + ((long long)b * Nq + qrow) * ldo + h * D;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(t_o + c * 32, r);
+      ptx::tmem_ld_wait();
+      if (qrow < Nq) {
+        uint4* o4 = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          o4[q] = make_uint4(pack2(__uint_as_float(r[8 * q]) * inv, __uint_as_float(r[8 * q + 1]) * inv),
+                             pack2(__uint_as_float(r[8 * q + 2]) * inv, __uint_as_float(r[8 * q + 3]) * inv),
+                             pack2(__uint_as_float(r[8 * q + 4]) * inv, __uint_as_float(r[8 * q + 5]) * inv),
+                             pack2(__uint_as_float(r[8 * q + 6]) * inv, __uint_as_float(r[8 * q + 7]) * inv));
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// tokens of one image: [N][ld] bf16 -> 3-D map {ld, N, B}, box {64, 128, 1}: rows past N are zero-filled
+static int make_map(CUtensorMap* m, const void* base, long long ld, int cols, int N, int B) {
+  EncodeTiledFn fn = get_encode();
+  if (!fn) { set_error("cuTensorMapEncodeTiled unavailable"); return D3R_ERR_CUDA; }
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)N, (cuuint64_t)B};
+  cuuint64_t str[2] = {(cuuint64_t)ld * 2, (cuuint64_t)N * ld * 2};
+  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("attention: cuTensorMapEncodeTiled failed (%d)", (int)r); return D3R_ERR_CUDA; }
+  return D3R_OK;
+}
+
+}  // namespace tc
+
+// q/k/v may be column slices of wider matrices (fused qkv / kv buffers): the map covers the whole matrix that
+// starts at the 16-byte aligned `*_base` pointer, the head column offset is added in the kernel.
+int attention_hd64_tc(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
+                      long long ldo, int B, int heads, int Nq, int Nk, float scale, cudaStream_t st) {
+  D3R_CHECK_ARG(q && k && v && out && B > 0 && heads > 0 && Nq > 0 && Nk > 0, "attention: bad arguments");
+  D3R_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "attention: row strides must be multiples of 8");
+  D3R_CHECK_ARG(((uintptr_t)q & 15) == 0 && ((uintptr_t)k & 15) == 0 && ((uintptr_t)v & 15) == 0 && ((uintptr_t)out & 15) == 0,
+                "attention: pointers must be 16-byte aligned");
+  CUtensorMap mq, mk, mv;
+  int rc;
+  if ((rc = tc::make_map(&mq, q, ldq, heads * 64, Nq, B))) return rc;
+  if ((rc = tc::make_map(&mk, k, ldk, heads * 64, Nk, B))) return rc;
+  if ((rc = tc::make_map(&mv, v, ldv, heads * 64, Nk, B))) return rc;
+  static bool attr = false;
+  if (!attr) {
+    D3R_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+    attr = true;
+  }
+  dim3 grid((Nq + tc::BQ - 1) / tc::BQ, heads, B);
+  prof::Scope scope("attention_tcgen05", st, 4.0 * double(B) * heads * double(Nq) * double(Nk) * 64.0);
+  tc::attention_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>(mq, mk, mv, (__nv_bfloat16*)out, ldo, Nq, Nk, 0, 0, 0,
+                                                                     scale * 1.4426950408889634f);
+  D3R_LAUNCH_CHECK();
+  return D3R_OK;
+}
+
+}  // namespace attn
+}  // namespace d3r

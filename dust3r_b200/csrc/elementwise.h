@@ -19,5 +19,8 @@ namespace attn {
 // q rows: (b*Nq + i)*ldq + h*64 ; k/v rows: (b*Nk + j)*ldk(v) + h*64.
 int attention_hd64(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
                    long long ldo, int B, int heads, int Nq, int Nk, float scale, cudaStream_t st);
+int attention_hd64_tc(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
+                      long long ldo, int B, int heads, int Nq, int Nk, float scale, cudaStream_t st);
+void set_impl(int impl);
 }  // namespace attn
 }  // namespace d3r

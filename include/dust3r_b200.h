@@ -170,6 +170,9 @@ int d3r_attention_hd64(const void* q_dev, int64_t ldq, const void* k_dev, int64_
                        void* out_dev, int64_t ldo, int32_t B, int32_t heads, int32_t Nq, int32_t Nk, float scale,
                        void* stream);
 
+/* Selects the attention kernel: 0 = mma.sync streaming kernel, 1 = tcgen05/TMEM kernel. */
+void d3r_set_attention_impl(int32_t impl);
+
 /* ------------------------------------------------------------------------------------------
  * Path 1 — pairwise forward: replaces AsymmetricCroCo3DStereo.forward (dust3r/model.py:199-211 =
  * _encode_symmetrized :153-170, _decoder :172-191, downstream heads :193-208) for one batch of

@@ -40,9 +40,11 @@ def _rel(a, b):
 
 
 @pytest.mark.timeout(600)
-def test_attention_matches_torch(cuda_device):
+@pytest.mark.parametrize('impl', [0, 1])
+def test_attention_matches_torch(cuda_device, impl):
     from dust3r_b200 import _lib
     lib = _lib.get_lib()
+    lib.d3r_set_attention_impl(impl)
     g = torch.Generator().manual_seed(0)
     for (B, Hh, Nq, Nk) in [(2, 3, 24, 24), (1, 2, 196, 196), (2, 4, 768, 768), (1, 2, 100, 37), (3, 1, 65, 130)]:
         q = torch.randn((B, Nq, Hh, 64), generator=g).to(cuda_device).bfloat16()
@@ -56,7 +58,10 @@ def test_attention_matches_torch(cuda_device):
         qf, kf, vf = [t.float().permute(0, 2, 1, 3) for t in (q, k, v)]
         ref = (torch.softmax(qf @ kf.transpose(-1, -2) * 0.125, dim=-1) @ vf).permute(0, 2, 1, 3)
         assert torch.isfinite(out.float()).all()
-        assert (out.float() - ref).abs().max().item() < 2e-2, (B, Hh, Nq, Nk)
+        err = (out.float() - ref).abs().max().item()
+        lib.d3r_set_attention_impl(0) if err >= 2e-2 else None
+        assert err < 2e-2, (impl, B, Hh, Nq, Nk, err)
+    lib.d3r_set_attention_impl(0)
 
 
 @pytest.mark.timeout(900)
