@@ -22,7 +22,7 @@ class AlignDesc(C.Structure):
     """Mirror of `d3r_align_desc` (include/dust3r_b200.h)."""
     _fields_ = [
         ('n_imgs', C.c_int32), ('n_edges', C.c_int32), ('n_entries', C.c_int32), ('n_chunks', C.c_int32),
-        ('max_deg', C.c_int32), ('max_chunks', C.c_int32), ('dist_l2', C.c_int32), ('norm_pw_scale', C.c_int32),
+        ('max_deg', C.c_int32), ('max_chunks', C.c_int32), ('chunk_px', C.c_int32), ('dist_l2', C.c_int32), ('norm_pw_scale', C.c_int32),
         ('tied_focal', C.c_int32), ('eval_only', C.c_int32),
         ('base_scale', C.c_float), ('pw_break', C.c_float), ('focal_break', C.c_float), ('adam_eps', C.c_float),
         ('beta1', C.c_float), ('beta2', C.c_float),

@@ -44,7 +44,8 @@ class AlignEngine:
         pix_off = np.zeros(n + 1, dtype=np.int64)
         pix_off[1:] = np.cumsum(self.pix_stride)
         self.pix_off = pix_off
-        chunk = self.lib.d3r_align_chunk_pixels()
+        chunk = self._pick_chunk_px(areas)
+        self.chunk_px = chunk
         nchunks = [(a + chunk - 1) // chunk for a in areas]
         chunk_ptr = np.zeros(n + 1, dtype=np.int32)
         chunk_ptr[1:] = np.cumsum(nchunks)
@@ -116,6 +117,22 @@ class AlignEngine:
         self.norm_pw_scale = True
         self.tied_focal = True
 
+    def _pick_chunk_px(self, areas):
+        """Pixels per CTA: the largest size <= the kernel's maximum for which the grid is (close to) a whole
+        number of waves of 2 CTAs/SM — a ragged last wave idles most of the chip for a full CTA lifetime."""
+        cmax = int(self.lib.d3r_align_chunk_pixels())
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        slots = 2 * sms
+        best, best_cost = cmax, None
+        for c in range(cmax, cmax // 2, -8):
+            total = sum((a + c - 1) // c for a in areas)
+            waves = total / slots
+            cost = math.ceil(waves) / waves            # time relative to a perfectly divisible grid
+            cost *= 1.0 + 0.02 * (cmax - c) / cmax      # mild preference for bigger chunks (fewer partial rows)
+            if best_cost is None or cost < best_cost - 1e-9:
+                best, best_cost = c, cost
+        return best
+
     # ------------------------------------------------------------------ parameters
     def algorithmic_bytes_per_iter(self):
         """32*E*P (observations read once) + 24*n*P (log-depth + 2 moments r/w)."""
@@ -183,6 +200,7 @@ class AlignEngine:
         d = _lib.AlignDesc()
         d.n_imgs, d.n_edges, d.n_entries, d.n_chunks = self.n, self.E, 2 * self.E, self.n_chunks
         d.max_deg, d.max_chunks = self.max_deg, self.max_chunks
+        d.chunk_px = self.chunk_px
         d.dist_l2 = 1 if self.dist == 'l2' else 0
         d.norm_pw_scale = int(self.norm_pw_scale)
         d.tied_focal = int(self.tied_focal)

@@ -344,13 +344,88 @@ __device__ void small_param_step(const d3r_align_desc& D, const Workspace& ws, i
 }
 
 // ---- the per-iteration kernel ---------------------------------------------------------------
+// 8 compute warps + 1 producer warp.  The producer streams each incident entry's float4 observations for
+// this CTA's pixel chunk into a 3-stage shared-memory ring with cp.async.bulk (TMA 1-D copies, mbarrier
+// completion), so ~2 x 96 KB of reads are in flight per SM independent of the compute warps' progress.
+constexpr int kStages = 3;
+constexpr int kEntTile = 16;               // entries whose per-warp partial sums are staged in smem at a time
+constexpr int kThreadsIter = kThreads + 32;
+constexpr int kRedVals = 16;               // 13 padded to 16 for the halving butterfly
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// Sum 16 per-lane values across the warp with 16 shuffles (instead of 16 x 5): at every halving step a lane
+// keeps one half of its values and trades the other half with its partner.  On return lane l holds the
+// warp-wide total of value index (l >> 1) & 15 in v[0].
+__device__ __forceinline__ float butterfly16(float (&v)[kRedVals], int lane) {
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float send = up ? v[i] : v[i + 8];
+      const float keep = up ? v[i + 8] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = up ? v[i] : v[i + 4];
+      const float keep = up ? v[i + 4] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = up ? v[i] : v[i + 2];
+      const float keep = up ? v[i + 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  {
+    const bool up = lane & 2;
+    const float send = up ? v[0] : v[1];
+    const float keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  return v[0];
+}
+
 template <bool kL2>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __maxnreg__(112)
 align_iter_kernel(const __grid_constant__ d3r_align_desc D, int it) {
-  extern __shared__ float s_ent[];  // [max_deg][kWarps][13]
+  extern __shared__ __align__(128) uint8_t s_dyn[];
+  float4* s_obs = reinterpret_cast<float4*>(s_dyn);                                  // [kStages][kChunk]
+  float* s_ent = reinterpret_cast<float*>(s_dyn + kStages * kChunk * sizeof(float4)); // [kEntTile][kWarps][13]
   __shared__ float s_img[kWarps * kImgVals];
   __shared__ float s_red[40];
   __shared__ int s_flag;
+  __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
 
   const Workspace ws = carve(D.workspace, D.n_imgs, D.n_edges, D.n_chunks, D.max_chunks);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -359,131 +434,159 @@ align_iter_kernel(const __grid_constant__ d3r_align_desc D, int it) {
   const int lc = chunk - D.img_chunk_ptr[img];
   const int H = D.img_hw[img * 2 + 0], W = D.img_hw[img * 2 + 1];
   const int P = H * W;
+  const int pbase = lc * D.chunk_px;                       // first pixel of this CTA
+  const int npx = min(D.chunk_px, P - pbase);              // >= 1
   const int64_t poff = D.img_pix_off[img];
-  const float* iT = ws.imgT + img * kImgT;
-  float R[9], T[3];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) R[k] = iT[k];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) T[k] = iT[9 + k];
-  const float ifx = iT[12], ify = iT[13], cx = iT[14], cy = iT[15];
-
-  float X[kPPT][3], G[kPPT][3];
-  const int p0 = lc * kChunk + tid;
-#pragma unroll
-  for (int k = 0; k < kPPT; ++k) {
-    const int p = p0 + k * kThreads;
-    const bool valid = p < P;
-    const float ld = valid ? D.logd[poff + p] : 0.f;
-    const float d = expf(ld);
-    const int v = p / W, u = p - v * W;
-    const float c0 = d * (float(u) - cx) * ifx, c1 = d * (float(v) - cy) * ify;
-    X[k][0] = R[0] * c0 + R[1] * c1 + R[2] * d + T[0];
-    X[k][1] = R[3] * c0 + R[4] * c1 + R[5] * d + T[1];
-    X[k][2] = R[6] * c0 + R[7] * c1 + R[8] * d + T[2];
-    G[k][0] = G[k][1] = G[k][2] = 0.f;
-  }
-
   const int e0 = D.img_ent_ptr[img], e1 = D.img_ent_ptr[img + 1];
+  const int deg = e1 - e0;
   const float4* obs_base = reinterpret_cast<const float4*>(D.obs);
-  for (int ent = e0; ent < e1; ++ent) {
-    const float* eT = ws.edgeT + D.ent_edge[ent] * kEdgeT;
-    float M[9], t[3];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) M[k] = eT[k];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) t[k] = eT[9 + k];
-    const float coef = D.ent_coef[ent];
-    const float4* obs = obs_base + D.ent_obs_off[ent];
-    float4 o[kPPT];
-#pragma unroll
-    for (int k = 0; k < kPPT; ++k) {
-      const int p = p0 + k * kThreads;
-      o[k] = (p < P) ? __ldcs(obs + p) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    float acc[kEntVals];
-#pragma unroll
-    for (int k = 0; k < kEntVals; ++k) acc[k] = 0.f;
-#pragma unroll
-    for (int k = 0; k < kPPT; ++k) {
-      const float qx = o[k].x, qy = o[k].y, qz = o[k].z;
-      const float lw = coef * o[k].w;
-      const float r0 = X[k][0] - (M[0] * qx + M[1] * qy + M[2] * qz + t[0]);
-      const float r1 = X[k][1] - (M[3] * qx + M[4] * qy + M[5] * qz + t[1]);
-      const float r2 = X[k][2] - (M[6] * qx + M[7] * qy + M[8] * qz + t[2]);
-      const float rho2 = r0 * r0 + r1 * r1 + r2 * r2;
-      float gs;
-      if (kL2) {
-        acc[12] += lw * rho2;
-        gs = 2.f * lw;
-      } else {
-        // torch's norm backward yields 0 at ||r|| == 0
-        const float inv = rho2 > 0.f ? rsqrtf(rho2) : 0.f;
-        acc[12] += lw * (rho2 * inv);
-        gs = lw * inv;
-      }
-      const float g0 = gs * r0, g1 = gs * r1, g2 = gs * r2;
-      G[k][0] += g0; G[k][1] += g1; G[k][2] += g2;
-      acc[0] += g0 * qx; acc[1] += g0 * qy; acc[2] += g0 * qz;
-      acc[3] += g1 * qx; acc[4] += g1 * qy; acc[5] += g1 * qz;
-      acc[6] += g2 * qx; acc[7] += g2 * qy; acc[8] += g2 * qz;
-      acc[9] += g0; acc[10] += g1; acc[11] += g2;
-    }
-#pragma unroll
-    for (int k = 0; k < kEntVals; ++k) acc[k] = warp_sum(acc[k]);
-    if (lane == 0) {
-      float* dst = s_ent + ((ent - e0) * kWarps + warp) * kEntVals;
-#pragma unroll
-      for (int k = 0; k < kEntVals; ++k) dst[k] = acc[k];
-    }
-  }
 
-  // depth gradient + Adam (in place), per-image pose/focal sums
-  float S[kImgVals];
-#pragma unroll
-  for (int k = 0; k < kImgVals; ++k) S[k] = 0.f;
-  {
-    const float step_size = D.sched[it * 4 + 1], bc2s = D.sched[it * 4 + 2];
-#pragma unroll
-    for (int k = 0; k < kPPT; ++k) {
-      const int p = p0 + k * kThreads;
-      if (p < P) {
-        if (D.eval_only) continue;
-        const float ld = D.logd[poff + p];
-        const float d = expf(ld);
-        const int v = p / W, u = p - v * W;
-        const float c0 = d * (float(u) - cx) * ifx, c1 = d * (float(v) - cy) * ify;
-        // dX/dlogd = R c  (c is linear in d)
-        const float gd = G[k][0] * (X[k][0] - T[0]) + G[k][1] * (X[k][1] - T[1]) + G[k][2] * (X[k][2] - T[2]);
-        float m = D.logd_m[poff + p], vv = D.logd_v[poff + p];
-        const float nld = adam_update(ld, gd, m, vv, D.beta1, D.beta2, step_size, bc2s, D.adam_eps);
-        D.logd[poff + p] = nld;
-        D.logd_m[poff + p] = m;
-        D.logd_v[poff + p] = vv;
-        S[0] += G[k][0] * c0; S[1] += G[k][0] * c1; S[2] += G[k][0] * d;
-        S[3] += G[k][1] * c0; S[4] += G[k][1] * c1; S[5] += G[k][1] * d;
-        S[6] += G[k][2] * c0; S[7] += G[k][2] * c1; S[8] += G[k][2] * d;
-        S[9] += G[k][0]; S[10] += G[k][1]; S[11] += G[k][2];
-      }
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(smem_u32(&s_full[s]), 1);
+      mbar_init(smem_u32(&s_empty[s]), kWarps);
     }
-  }
-#pragma unroll
-  for (int k = 0; k < kImgVals; ++k) S[k] = warp_sum(S[k]);
-  if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < kImgVals; ++k) s_img[warp * kImgVals + k] = S[k];
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  // cross-warp sums -> partial rows in global memory
-  const int deg = e1 - e0;
-  for (int idx = tid; idx < deg * kEntVals; idx += kThreads) {
-    const int k = idx / kEntVals, v = idx - k * kEntVals;
-    float s = 0.f;
+  if (warp == kWarps) {
+    // ================= producer warp =================
+    if (lane == 0) {
+      const uint32_t bytes = uint32_t(npx) * 16u;
+      for (int k = 0; k < deg; ++k) {
+        const int s = k % kStages;
+        const uint32_t ph = (k / kStages) & 1;
+        mbar_wait(smem_u32(&s_empty[s]), ph ^ 1);
+        mbar_expect_tx(smem_u32(&s_full[s]), bytes);
+        bulk_g2s(smem_u32(s_obs + s * kChunk), obs_base + D.ent_obs_off[e0 + k] + pbase, bytes, smem_u32(&s_full[s]));
+      }
+    }
+  } else {
+    // ================= compute warps =================
+    const float* iT = ws.imgT + img * kImgT;
+    float R[9], T[3];
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) s += s_ent[(k * kWarps + w) * kEntVals + v];
-    __stcg(ws.ent_part + (int64_t(e0 + k) * D.max_chunks + lc) * kEntVals + v, s);
+    for (int k = 0; k < 9; ++k) R[k] = iT[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) T[k] = iT[9 + k];
+    const float ifx = iT[12], ify = iT[13], cx = iT[14], cy = iT[15];
+
+    float X[kPPT][3], G[kPPT][3];
+#pragma unroll
+    for (int k = 0; k < kPPT; ++k) {
+      const int q = tid + k * kThreads;
+      const int p = pbase + q;
+      const float ld = (q < npx) ? D.logd[poff + p] : 0.f;
+      const float d = expf(ld);
+      const int v = p / W, u = p - v * W;
+      const float c0 = d * (float(u) - cx) * ifx, c1 = d * (float(v) - cy) * ify;
+      X[k][0] = R[0] * c0 + R[1] * c1 + R[2] * d + T[0];
+      X[k][1] = R[3] * c0 + R[4] * c1 + R[5] * d + T[1];
+      X[k][2] = R[6] * c0 + R[7] * c1 + R[8] * d + T[2];
+      G[k][0] = G[k][1] = G[k][2] = 0.f;
+    }
+
+    for (int k0 = 0; k0 < deg; k0 += kEntTile) {
+      const int kend = min(deg, k0 + kEntTile);
+      for (int kk = k0; kk < kend; ++kk) {
+        const int ent = e0 + kk;
+        const float* eT = ws.edgeT + D.ent_edge[ent] * kEdgeT;
+        float M[9], t[3];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) M[k] = eT[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) t[k] = eT[9 + k];
+        const float coef = D.ent_coef[ent];
+        const int s = kk % kStages;
+        mbar_wait(smem_u32(&s_full[s]), (kk / kStages) & 1);
+        const float4* so = s_obs + s * kChunk;
+        float acc[kRedVals];
+#pragma unroll
+        for (int k = 0; k < kRedVals; ++k) acc[k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < kPPT; ++k) {
+          const int q = tid + k * kThreads;
+          float4 o = so[q];
+          if (q >= npx) o = make_float4(0.f, 0.f, 0.f, 0.f);   // stale smem beyond the chunk: force weight 0
+          const float qx = o.x, qy = o.y, qz = o.z;
+          const float lw = coef * o.w;
+          const float r0 = X[k][0] - (M[0] * qx + M[1] * qy + M[2] * qz + t[0]);
+          const float r1 = X[k][1] - (M[3] * qx + M[4] * qy + M[5] * qz + t[1]);
+          const float r2 = X[k][2] - (M[6] * qx + M[7] * qy + M[8] * qz + t[2]);
+          const float rho2 = r0 * r0 + r1 * r1 + r2 * r2;
+          float gs;
+          if (kL2) {
+            acc[12] += lw * rho2;
+            gs = 2.f * lw;
+          } else {
+            // torch's norm backward yields 0 at ||r|| == 0
+            const float inv = rho2 > 0.f ? rsqrtf(rho2) : 0.f;
+            acc[12] += lw * (rho2 * inv);
+            gs = lw * inv;
+          }
+          const float g0 = gs * r0, g1 = gs * r1, g2 = gs * r2;
+          G[k][0] += g0; G[k][1] += g1; G[k][2] += g2;
+          acc[0] += g0 * qx; acc[1] += g0 * qy; acc[2] += g0 * qz;
+          acc[3] += g1 * qx; acc[4] += g1 * qy; acc[5] += g1 * qz;
+          acc[6] += g2 * qx; acc[7] += g2 * qy; acc[8] += g2 * qz;
+          acc[9] += g0; acc[10] += g1; acc[11] += g2;
+        }
+        // this warp is done with the stage: hand it back to the producer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&s_empty[s]));
+        const float tot = butterfly16(acc, lane);
+        const int vi = (lane >> 1) & 15;
+        if (!(lane & 1) && vi < kEntVals) s_ent[((kk - k0) * kWarps + warp) * kEntVals + vi] = tot;
+      }
+      // cross-warp sums of this tile of entries -> partial rows in global memory (fixed order)
+      asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+      for (int idx = tid; idx < (kend - k0) * kEntVals; idx += kThreads) {
+        const int k = idx / kEntVals, v = idx - k * kEntVals;
+        float sacc = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) sacc += s_ent[(k * kWarps + w) * kEntVals + v];
+        __stcg(ws.ent_part + (int64_t(e0 + k0 + k) * D.max_chunks + lc) * kEntVals + v, sacc);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+    }
+
+    // depth gradient + Adam (in place), per-image pose/focal sums
+    float S[kRedVals];
+#pragma unroll
+    for (int k = 0; k < kRedVals; ++k) S[k] = 0.f;
+    if (!D.eval_only) {
+      const float step_size = D.sched[it * 4 + 1], bc2s = D.sched[it * 4 + 2];
+#pragma unroll
+      for (int k = 0; k < kPPT; ++k) {
+        const int q = tid + k * kThreads;
+        if (q < npx) {
+          const int p = pbase + q;
+          const float ld = D.logd[poff + p];
+          const float d = expf(ld);
+          const int v = p / W, u = p - v * W;
+          const float c0 = d * (float(u) - cx) * ifx, c1 = d * (float(v) - cy) * ify;
+          // dX/dlogd = R c  (c is linear in d)
+          const float gd = G[k][0] * (X[k][0] - T[0]) + G[k][1] * (X[k][1] - T[1]) + G[k][2] * (X[k][2] - T[2]);
+          float m = D.logd_m[poff + p], vv = D.logd_v[poff + p];
+          const float nld = adam_update(ld, gd, m, vv, D.beta1, D.beta2, step_size, bc2s, D.adam_eps);
+          D.logd[poff + p] = nld;
+          D.logd_m[poff + p] = m;
+          D.logd_v[poff + p] = vv;
+          S[0] += G[k][0] * c0; S[1] += G[k][0] * c1; S[2] += G[k][0] * d;
+          S[3] += G[k][1] * c0; S[4] += G[k][1] * c1; S[5] += G[k][1] * d;
+          S[6] += G[k][2] * c0; S[7] += G[k][2] * c1; S[8] += G[k][2] * d;
+          S[9] += G[k][0]; S[10] += G[k][1]; S[11] += G[k][2];
+        }
+      }
+    }
+    {
+      const float tot = butterfly16(S, lane);
+      const int vi = (lane >> 1) & 15;
+      if (!(lane & 1) && vi < kImgVals) s_img[warp * kImgVals + vi] = tot;
+    }
   }
+  __syncthreads();
   if (tid < kImgVals) {
     float s = 0.f;
 #pragma unroll
@@ -499,7 +602,7 @@ align_iter_kernel(const __grid_constant__ d3r_align_desc D, int it) {
   __syncthreads();
   if (!s_flag) return;
   __threadfence();
-  for (int idx = tid; idx < deg * kEntVals; idx += kThreads) {
+  for (int idx = tid; idx < deg * kEntVals; idx += kThreadsIter) {
     const int k = idx / kEntVals, v = idx - k * kEntVals;
     const float* src = ws.ent_part + int64_t(e0 + k) * D.max_chunks * kEntVals + v;
     float s = 0.f;
@@ -534,9 +637,8 @@ __global__ void __launch_bounds__(kThreads) pts3d_kernel(const __grid_constant__
   const int P = H * W;
   const int64_t poff = D.img_pix_off[img];
   const float* iT = ws.imgT + img * kImgT;
-  for (int k = 0; k < kPPT; ++k) {
-    const int p = lc * kChunk + k * kThreads + threadIdx.x;
-    if (p >= P) continue;
+  const int pend = min(P, (lc + 1) * D.chunk_px);
+  for (int p = lc * D.chunk_px + threadIdx.x; p < pend; p += kThreads) {
     const float d = expf(D.logd[poff + p]);
     const int v = p / W, u = p - v * W;
     const float c0 = d * (float(u) - iT[14]) * iT[12], c1 = d * (float(v) - iT[15]) * iT[13];
@@ -573,8 +675,7 @@ static int validate(const d3r_align_desc* d) {
   D3R_CHECK_ARG(d->obs && d->logd && d->logd_m && d->logd_v && d->small && d->small_m && d->small_v &&
                     d->small_trainable && d->workspace && d->sched && d->loss_out && d->counters,
                 "d3r_align: null buffer");
-  D3R_CHECK_ARG(size_t(d->max_deg) * kWarps * kEntVals * sizeof(float) <= 200 * 1024,
-                "d3r_align: image degree %d too large for the shared-memory reduction", d->max_deg);
+  D3R_CHECK_ARG(d->chunk_px > 0 && d->chunk_px <= kChunk, "d3r_align: chunk_px=%d must be in [1, %d]", d->chunk_px, kChunk);
   return D3R_OK;
 }
 
@@ -590,7 +691,7 @@ extern "C" int d3r_align_run(const d3r_align_desc* desc, int32_t it_begin, int32
   int rc = validate(desc);
   if (rc) return rc;
   D3R_CHECK_ARG(it_begin >= 0 && it_end >= it_begin, "d3r_align_run: bad iteration range");
-  const size_t smem = size_t(desc->max_deg) * kWarps * kEntVals * sizeof(float);
+  const size_t smem = size_t(kStages) * kChunk * sizeof(float4) + size_t(kEntTile) * kWarps * kEntVals * sizeof(float);
   if (desc->dist_l2) {
     D3R_CUDA(cudaFuncSetAttribute(align_iter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   } else {
@@ -599,9 +700,9 @@ extern "C" int d3r_align_run(const d3r_align_desc* desc, int32_t it_begin, int32
   prof::Scope scope("align_iter", (cudaStream_t)stream, 0.0, 0.0, it_end - it_begin);
   for (int it = it_begin; it < it_end; ++it) {
     if (desc->dist_l2)
-      align_iter_kernel<true><<<desc->n_chunks, kThreads, smem, (cudaStream_t)stream>>>(*desc, it);
+      align_iter_kernel<true><<<desc->n_chunks, kThreadsIter, smem, (cudaStream_t)stream>>>(*desc, it);
     else
-      align_iter_kernel<false><<<desc->n_chunks, kThreads, smem, (cudaStream_t)stream>>>(*desc, it);
+      align_iter_kernel<false><<<desc->n_chunks, kThreadsIter, smem, (cudaStream_t)stream>>>(*desc, it);
   }
   D3R_LAUNCH_CHECK();
   return D3R_OK;

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(kThreads) attention_kernel(const __nv_bfloat16
   }
 }
 
-static int g_impl = 0;  // 0: mma.sync streaming kernel, 1: tcgen05/TMEM kernel (attention_tc.cu)
+static int g_impl = 1;  // 1: tcgen05/TMEM kernel (attention_tc.cu, default), 0: mma.sync streaming kernel (A/B reference)
 void set_impl(int impl) { g_impl = impl; }
 
 int attention_hd64(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,

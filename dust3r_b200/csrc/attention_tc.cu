@@ -26,8 +26,9 @@ namespace tc {
 constexpr int BQ = 128, BK = 128, D = 64;
 constexpr int kThreads = 192;
 constexpr int kTileBytes = 128 * 64 * 2;  // 16 KB: 128 rows x 128 B
-constexpr int kSmemBytes = 1024 /*align*/ + kTileBytes /*Q*/ + 2 * kTileBytes /*K ring*/ + 2 * kTileBytes /*V ring*/ +
-                           2 * kTileBytes /*P: two 64-key atoms*/ + 256 /*barriers*/;
+// 7 tiles + barriers = 112.1 KB: two CTAs (+1 KB reserved each) fit the 228 KB of an SM
+constexpr int kSmemBytes = kTileBytes /*Q*/ + 2 * kTileBytes /*K ring*/ + 2 * kTileBytes /*V ring*/ +
+                           2 * kTileBytes /*P: two 64-key atoms*/ + 128 /*barriers*/;
 constexpr int kTmemCols = 256;
 constexpr uint32_t kColS = 0, kColO = 128;
 
@@ -70,8 +71,8 @@ __global__ void __launch_bounds__(kThreads, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const __grid_constant__ CUtensorMap tmap_v, __nv_bfloat16* __restrict__ out, long long ldo, int Nq, int Nk,
                     int q_col0, int k_col0, int v_col0, float scale_log2) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];   // 128B-swizzle atoms need 1024-byte alignment
+  if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
   uint8_t* s_q = smem;
   uint8_t* s_k = s_q + kTileBytes;
   uint8_t* s_v = s_k + 2 * kTileBytes;

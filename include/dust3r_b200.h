@@ -67,9 +67,11 @@ typedef struct d3r_align_desc {
   int32_t n_imgs;          /* n                                                             */
   int32_t n_edges;         /* E (directed edges, base_opt.py:61)                            */
   int32_t n_entries;       /* 2*E : one entry per (edge, side)                              */
-  int32_t n_chunks;        /* total CTAs = sum_i ceil(P_i / d3r_align_chunk_pixels())       */
+  int32_t n_chunks;        /* total CTAs = sum_i ceil(P_i / chunk_px)                       */
   int32_t max_deg;         /* max entries incident to one image                             */
   int32_t max_chunks;      /* max CTAs of one image                                         */
+  int32_t chunk_px;        /* pixels per CTA, 1..d3r_align_chunk_pixels() (host picks it so
+                              the grid is a whole number of waves)                          */
   int32_t dist_l2;         /* 0: l1_dist, 1: l2_dist (commons.py:62-70)                     */
   int32_t norm_pw_scale;   /* base_opt.py:86,178-184                                        */
   int32_t tied_focal;      /* 1: one focal per image (fx==fy), 0: fx_and_fy                 */
@@ -115,7 +117,7 @@ typedef struct d3r_align_desc {
 
 /* sizeof(d3r_align_desc) as compiled into the library (binding self-check). */
 int d3r_sizeof_align_desc(void);
-/* Pixels handled by one CTA of the alignment kernel (a compile-time constant of the library). */
+/* Maximum pixels one CTA of the alignment kernel can take (compile-time constant of the library). */
 int d3r_align_chunk_pixels(void);
 /* Number of floats of `workspace` needed for a problem of this size. */
 int64_t d3r_align_workspace_floats(int32_t n_imgs, int32_t n_edges, int32_t n_chunks, int32_t max_chunks);
