@@ -344,12 +344,13 @@ __device__ void small_param_step(const d3r_align_desc& D, const Workspace& ws, i
 }
 
 // ---- the per-iteration kernel ---------------------------------------------------------------
-// 8 compute warps + 1 producer warp.  The producer streams each incident entry's float4 observations for
-// this CTA's pixel chunk into a 3-stage shared-memory ring with cp.async.bulk (TMA 1-D copies, mbarrier
-// completion), so ~2 x 96 KB of reads are in flight per SM independent of the compute warps' progress.
+// 8 warps, all computing; lane 0 of warp 0 doubles as the producer: each incident entry's float4 observations
+// for this CTA's pixel chunk are streamed into a 3-stage shared-memory ring with cp.async.bulk (TMA 1-D copies,
+// mbarrier completion), refilled as soon as a stage is drained, so up to 2 x 84 KB of reads are in flight per
+// SM independent of the warps' compute progress.
 constexpr int kStages = 3;
 constexpr int kEntTile = 16;               // entries whose per-warp partial sums are staged in smem at a time
-constexpr int kThreadsIter = kThreads + 32;
+constexpr int kThreadsIter = kThreads;      // 8 warps (warp allocation granularity is 4: a 9th warp would cost a whole CTA/SM)
 constexpr int kRedVals = 16;               // 13 padded to 16 for the halving butterfly
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -417,7 +418,7 @@ __device__ __forceinline__ float butterfly16(float (&v)[kRedVals], int lane) {
 }
 
 template <bool kL2>
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(kThreadsIter, 2)
 align_iter_kernel(const __grid_constant__ d3r_align_desc D, int it) {
   extern __shared__ __align__(128) uint8_t s_dyn[];
   float4* s_obs = reinterpret_cast<float4*>(s_dyn);                                  // [kStages][kChunk]
@@ -450,19 +451,16 @@ align_iter_kernel(const __grid_constant__ d3r_align_desc D, int it) {
   }
   __syncthreads();
 
-  if (warp == kWarps) {
-    // ================= producer warp =================
-    if (lane == 0) {
-      const uint32_t bytes = uint32_t(npx) * 16u;
-      for (int k = 0; k < deg; ++k) {
-        const int s = k % kStages;
-        const uint32_t ph = (k / kStages) & 1;
-        mbar_wait(smem_u32(&s_empty[s]), ph ^ 1);
-        mbar_expect_tx(smem_u32(&s_full[s]), bytes);
-        bulk_g2s(smem_u32(s_obs + s * kChunk), obs_base + D.ent_obs_off[e0 + k] + pbase, bytes, smem_u32(&s_full[s]));
-      }
-    }
-  } else {
+  const uint32_t stage_bytes = uint32_t(npx) * 16u;
+  auto produce = [&](int k) {   // called by one thread
+    const int s = k % kStages;
+    mbar_wait(smem_u32(&s_empty[s]), ((k / kStages) & 1) ^ 1);
+    mbar_expect_tx(smem_u32(&s_full[s]), stage_bytes);
+    bulk_g2s(smem_u32(s_obs + s * kChunk), obs_base + D.ent_obs_off[e0 + k] + pbase, stage_bytes, smem_u32(&s_full[s]));
+  };
+  if (tid == 0)
+    for (int k = 0; k < min(kStages, deg); ++k) produce(k);
+  {
     // ================= compute warps =================
     const float* iT = ws.imgT + img * kImgT;
     float R[9], T[3];
@@ -535,6 +533,7 @@ align_iter_kernel(const __grid_constant__ d3r_align_desc D, int it) {
         // this warp is done with the stage: hand it back to the producer
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&s_empty[s]));
+        if (tid == 0 && kk + kStages < deg) produce(kk + kStages);   // refill the stage just drained
         const float tot = butterfly16(acc, lane);
         const int vi = (lane >> 1) & 15;
         if (!(lane & 1) && vi < kEntVals) s_ent[((kk - k0) * kWarps + warp) * kEntVals + vi] = tot;
@@ -694,8 +693,10 @@ extern "C" int d3r_align_run(const d3r_align_desc* desc, int32_t it_begin, int32
   const size_t smem = size_t(kStages) * kChunk * sizeof(float4) + size_t(kEntTile) * kWarps * kEntVals * sizeof(float);
   if (desc->dist_l2) {
     D3R_CUDA(cudaFuncSetAttribute(align_iter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    D3R_CUDA(cudaFuncSetAttribute(align_iter_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   } else {
     D3R_CUDA(cudaFuncSetAttribute(align_iter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    D3R_CUDA(cudaFuncSetAttribute(align_iter_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   }
   prof::Scope scope("align_iter", (cudaStream_t)stream, 0.0, 0.0, it_end - it_begin);
   for (int it = it_begin; it < it_end; ++it) {

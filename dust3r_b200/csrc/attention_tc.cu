@@ -7,9 +7,10 @@
 //   warp 0      TMA producer : Q tile once, then K_j / V_j (128 keys x 64) into 2-deep 128B-swizzled rings
 //   warp 1      MMA issuer   : S = Q K_j^T  (UMMA 128x128x16 x4, K-major A and B)  -> TMEM cols [0,128)
 //                              O += P V_j   (UMMA 128x64x16 x8, A = P from smem, B = V_j MN-major) -> cols [128,192)
-//   warps 2..5  softmax      : thread = query row.  tcgen05.ld S -> running max / exp2 / row sum -> P (bf16)
-//                              written to smem in the canonical K-major SW128 layout; rescales O in TMEM
-//                              (tcgen05.ld/st) when the running max moves; final 1/l normalisation + store.
+//   warps 2..5  softmax      : thread = query row.  one tcgen05.ld pass pulls the S row into registers (S is
+//                              released at once), max / exp2 / row sum -> P (bf16) stored to smem in the canonical
+//                              K-major SW128 layout; O in TMEM is rescaled lazily (only when the running max grew
+//                              by more than 2^8); final 1/l normalisation + store.
 // Keys beyond Nk are masked to -inf (TMA zero-fills rows past the image because the tensor maps are 3-D
 // {cols, tokens, images}).
 #include "d3r_common.cuh"
@@ -181,68 +182,52 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
     const uint32_t t_s = tmem_base + lane_addr + kColS, t_o = tmem_base + lane_addr + kColO;
-    float m = -INFINITY, l = 0.f;
+    // m_ref: the exponent reference currently baked into O and l.  It only follows the true running max when
+    // that max has moved by more than 2^kLazy (lazy rescaling): p may then exceed 1 by at most 2^kLazy, which
+    // fp32 sums / bf16 P absorb, and the tcgen05.ld/st round trip over O is skipped for most blocks.
+    constexpr float kLazy = 8.f;
+    float m_ref = -INFINITY, l = 0.f;
     for (int j = 0; j < nblk; ++j) {
       const int nvalid = min(BK, Nk - j * BK);
       ptx::mbar_wait(ptx::smem_u32(s_ready), j & 1);
       ptx::tc_fence_after();
-      // pass 1: row max
-      float mx = m;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        if (c * 32 >= nvalid) break;
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(t_s + c * 32, r);
-        ptx::tmem_ld_wait();
+      // whole S row -> registers (single TMEM pass), then release S for the next Q K^T immediately
+      uint32_t sr[128];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float v = (c * 32 + i < nvalid) ? __uint_as_float(r[i]) : -INFINITY;
-          mx = fmaxf(mx, v);
+      for (int c = 0; c < 4; ++c) ptx::tmem_ld_32x32b_x32(t_s + c * 32, sr + c * 32);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(s_free));
+      float mx = -INFINITY;
+      if (nvalid == BK) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(sr[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 128; ++i) {
+          if (i >= nvalid) sr[i] = 0xff800000u;  // -inf
+          mx = fmaxf(mx, __uint_as_float(sr[i]));
         }
       }
-      const float corr = exp2f((m - mx) * scale_log2);  // 0 on the first block (m = -inf)
-      const float ms = mx * scale_log2;
-      m = mx;
+      // rescale decision (warp-uniform so the tcgen05.ld/st below stay convergent)
+      const bool grow = (mx - m_ref) * scale_log2 > kLazy;
+      const bool rescale = (j > 0) && __any_sync(0xffffffffu, grow);
+      float corr = 1.f;
+      if (j == 0) {
+        m_ref = mx;
+      } else if (rescale) {
+        const float m_new = fmaxf(m_ref, mx);
+        corr = fast_exp2((m_ref - m_new) * scale_log2);
+        m_ref = m_new;
+      }
+      const float ms = m_ref * scale_log2;
       // the previous P V must have consumed P (smem) and updated O before we touch either
       if (j > 0) {
         ptx::mbar_wait(ptx::smem_u32(o_done), (j - 1) & 1);
         ptx::tc_fence_after();
       }
-      // pass 2: p = exp2(s*c - m*c), row sum, bf16 pack, swizzled store (K-major SW128: 16-B chunk ^ (row & 7))
-      float rs = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t packed[16];
-        if (c * 32 < nvalid) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(t_s + c * 32, r);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = (c * 32 + i < nvalid) ? fast_exp2(__uint_as_float(r[i]) * scale_log2 - ms) : 0.f;
-            const float p1 = (c * 32 + i + 1 < nvalid) ? fast_exp2(__uint_as_float(r[i + 1]) * scale_log2 - ms) : 0.f;
-            rs += p0 + p1;
-            packed[i >> 1] = pack2(p0, p1);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) packed[i] = 0u;
-        }
-        uint8_t* atom = s_p + (c >> 1) * kTileBytes + row * 128;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = (c & 1) * 4 + q;
-          *reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) =
-              make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-        }
-      }
-      // S_j fully read -> the MMA warp may overwrite it with S_{j+1}
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(s_free));
-      l = l * corr + rs;
-      // rescale the running output
-      if (j > 0) {
+      if (rescale) {
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
           uint32_t r[32];
@@ -254,6 +239,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         }
         tmem_st_wait();
       }
+      // p = exp2(s*c - m_ref*c), row sum, bf16 pack, swizzled store (K-major SW128: 16-B chunk ^ (row & 7))
+      float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[c * 32 + i]), scale_log2, -ms));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[c * 32 + i + 1]), scale_log2, -ms));
+          rs0 += p0;
+          rs1 += p1;
+          packed[i >> 1] = pack2(p0, p1);
+        }
+        uint8_t* atom = s_p + (c >> 1) * kTileBytes + row * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = (c & 1) * 4 + q;
+          *reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) =
+              make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        }
+      }
+      l = l * corr + (rs0 + rs1);
       // make the generic-proxy smem writes of P visible to the tensor core (async proxy), then publish
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
