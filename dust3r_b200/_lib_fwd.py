@@ -54,6 +54,8 @@ def declare(lib):
     lib.d3r_conv3x3_bf16.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, u32, vp]
     lib.d3r_attention_hd64.restype = C.c_int
     lib.d3r_attention_hd64.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, f32, vp]
+    lib.d3r_set_gemm_impl.restype = None
+    lib.d3r_set_gemm_impl.argtypes = [i32]
     lib.d3r_set_attention_impl.restype = None
     lib.d3r_set_attention_impl.argtypes = [i32]
     lib.d3r_forward_workspace_bytes.restype = i64

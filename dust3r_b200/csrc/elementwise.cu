@@ -147,28 +147,26 @@ int patch_im2col16(const float* img, void* out, int B, int H, int W, cudaStream_
 }
 
 // ---- bilinear x2 upsample, align_corners=True, NHWC bf16 (F.interpolate in dpt_block.py:226,247) ----
-__global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int H, int W,
-                                  int C, int Ho, int Wo) {
-  const int vpc = C / 8;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t total = (size_t)B * Ho * Wo * vpc;
-  if (idx >= total) return;
-  const int v = (int)(idx % vpc);
-  size_t pix = idx / vpc;
-  const int ox = (int)(pix % Wo);
-  pix /= Wo;
-  const int oy = (int)(pix % Ho);
-  const int b = (int)(pix / Ho);
+__global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                          int H, int W, int C, int Ho, int Wo, int vpc_shift) {
+  // grid = (x tiles, Ho, B): the row interpolation terms are block-uniform, no per-thread div/mod chain
+  const int oy = blockIdx.y, b = blockIdx.z;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int vpc = 1 << vpc_shift;
+  const int ox = idx >> vpc_shift, v = idx & (vpc - 1);
+  if (ox >= Wo) return;
   // source coordinate for an output grid of (2H, 2W) (cropping keeps the scale of the full map)
   const float sy = (H > 1) ? oy * (float(H - 1) / float(2 * H - 1)) : 0.f;
   const float sx = (W > 1) ? ox * (float(W - 1) / float(2 * W - 1)) : 0.f;
   const int y0 = (int)sy, x0 = (int)sx;
   const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
   const float fy = sy - y0, fx = sx - x0;
-  const uint4 p00 = *reinterpret_cast<const uint4*>(x + (((size_t)b * H + y0) * W + x0) * C + v * 8);
-  const uint4 p01 = *reinterpret_cast<const uint4*>(x + (((size_t)b * H + y0) * W + x1) * C + v * 8);
-  const uint4 p10 = *reinterpret_cast<const uint4*>(x + (((size_t)b * H + y1) * W + x0) * C + v * 8);
-  const uint4 p11 = *reinterpret_cast<const uint4*>(x + (((size_t)b * H + y1) * W + x1) * C + v * 8);
+  const __nv_bfloat16* r0 = x + ((size_t)b * H + y0) * W * C + v * 8;
+  const __nv_bfloat16* r1 = x + ((size_t)b * H + y1) * W * C + v * 8;
+  const uint4 p00 = __ldg(reinterpret_cast<const uint4*>(r0 + (size_t)x0 * C));
+  const uint4 p01 = __ldg(reinterpret_cast<const uint4*>(r0 + (size_t)x1 * C));
+  const uint4 p10 = __ldg(reinterpret_cast<const uint4*>(r1 + (size_t)x0 * C));
+  const uint4 p11 = __ldg(reinterpret_cast<const uint4*>(r1 + (size_t)x1 * C));
   const uint32_t a[4] = {p00.x, p00.y, p00.z, p00.w}, bq[4] = {p01.x, p01.y, p01.z, p01.w};
   const uint32_t c[4] = {p10.x, p10.y, p10.z, p10.w}, d[4] = {p11.x, p11.y, p11.z, p11.w};
   uint32_t r[4];
@@ -183,13 +181,18 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bflo
     const float hi = w00 * __high2float(ha) + w01 * __high2float(hb) + w10 * __high2float(hc) + w11 * __high2float(hd);
     r[t] = pack2(lo, hi);
   }
-  *reinterpret_cast<uint4*>(out + (((size_t)b * Ho + oy) * Wo + ox) * C + v * 8) = make_uint4(r[0], r[1], r[2], r[3]);
+  __stcs(reinterpret_cast<uint4*>(out + (((size_t)b * Ho + oy) * Wo + ox) * C + v * 8), make_uint4(r[0], r[1], r[2], r[3]));
 }
 int upsample2x_bf16(const void* x, void* out, int B, int H, int W, int C, int Ho, int Wo, cudaStream_t st) {
   D3R_CHECK_ARG(C % 8 == 0 && Ho <= 2 * H && Wo <= 2 * W, "upsample2x: bad shape");
-  const size_t total = (size_t)B * Ho * Wo * (C / 8);
+  const int vpc = C / 8;
+  D3R_CHECK_ARG((vpc & (vpc - 1)) == 0, "upsample2x: C/8 must be a power of two (C=%d)", C);
+  int shift = 0;
+  while ((1 << shift) < vpc) ++shift;
+  const size_t total = (size_t)B * Ho * Wo * vpc;
   prof::Scope scope("upsample2x", st, 0.0, double(total) * 20.0);
-  upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, B, H, W, C, Ho, Wo);
+  dim3 grid((unsigned)(((size_t)Wo * vpc + 255) / 256), (unsigned)Ho, (unsigned)B);
+  upsample2x_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, H, W, C, Ho, Wo, shift);
   D3R_LAUNCH_CHECK();
   return D3R_OK;
 }

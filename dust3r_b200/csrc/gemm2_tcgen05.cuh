@@ -1,0 +1,356 @@
+// 2-CTA (cta_group::2) variant of the persistent tcgen05 GEMM / implicit-GEMM conv kernel.
+//
+// A CTA pair (cluster of 2, same TPC) computes a 256 x BLOCK_N tile: each CTA stages its own 128 rows of A
+// and HALF of the B tile (BLOCK_N/2 rows), the pair leader issues tcgen05.mma.cta_group::2 (UMMA M=256) and
+// the hardware reads the two B halves from both CTAs' shared memory.  Per CTA and k-block that is 16 KB (A)
+// + 16 KB (B/2) staged instead of 16 + 32 KB: shared-memory traffic (TMA writes + UMMA operand reads) drops by
+// a third, which is what bounds the 1-CTA kernel (tensor pipe 67 % busy at 192 B/clk of smem traffic), and the
+// ring gets 6 stages instead of 4.  TMA loads of both CTAs signal the LEADER's full barrier
+// (.cta_group::2, peer-bit-masked mbarrier address); tcgen05.commit multicasts to both CTAs' empty / tmem-full
+// barriers; both CTAs' epilogue warps arrive on the leader's tmem-empty barrier (mapa + remote arrive).
+// Generated from the same role structure / fused epilogues as gemm_tcgen05.cuh (see there).
+#pragma once
+#include "gemm_tcgen05.cuh"
+
+namespace d3r {
+namespace gemm {
+
+template <int BLOCK_N>
+struct Cfg2 {
+  static constexpr int kStageA = BLOCK_M * BLOCK_K * 2;
+  static constexpr int kStageB = (BLOCK_N / 2) * BLOCK_K * 2;
+  static constexpr int kStages = (BLOCK_N >= 256) ? 6 : 8;
+  static constexpr int kTmemCols = (2 * BLOCK_N <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * (kStageA + kStageB) + 1024 /*align*/ + 256 /*barriers*/ + 4 * 128 * 4 + 64;
+};
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+  using C = Cfg2<BLOCK_N>;
+  const uint32_t cta_rank = ptx::cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::kStages * C::kStageA;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * (C::kStageA + C::kStageB));
+  uint64_t* full_bar = bars;                      // [kStages]
+  uint64_t* empty_bar = bars + C::kStages;        // [kStages]
+  uint64_t* tfull_bar = bars + 2 * C::kStages;    // [2]
+  uint64_t* tempty_bar = bars + 2 * C::kStages + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
+  float* s_w4 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [4][128] + [4]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int m_tiles = (p.mode == 1) ? p.cB * p.tiles_y * p.tiles_x : (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int m_tiles2 = (m_tiles + 1) / 2;            // 256-row cluster tiles
+  const int total_tiles = m_tiles2 * n_tiles;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&tfull_bar[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&tempty_bar[s]), 2 * kNumEpilogueWarps);   // both CTAs' epilogue warps
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    __syncwarp();
+    ptx::tmem_alloc2(ptx::smem_u32(tmem_slot), C::kTmemCols);
+    ptx::tmem_relinquish2();
+  }
+  if ((p.flags & F_HEAD_FINAL) && threadIdx.x >= 64) {
+    for (int i = threadIdx.x - 64; i < 4 * 128 + 4; i += 32 * kNumEpilogueWarps) s_w4[i] = (i < 512) ? p.w4[i] : p.b4[i - 512];
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        const int tn = tile % n_tiles, tm = (tile / n_tiles) * 2 + int(cta_rank);
+        int cb = 0, cy0 = 0, cx0 = 0;
+        if (p.mode == 1) {
+          cb = tm / (p.tiles_y * p.tiles_x);
+          const int r = tm - cb * (p.tiles_y * p.tiles_x);
+          cy0 = (r / p.tiles_x) * p.tile_h;
+          cx0 = (r % p.tiles_x) * p.tile_w;
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = ptx::smem_u32(&full_bar[stage]) & 0xFEFFFFFFu;   // the pair leader's barrier
+          if (leader) ptx::mbar_arrive_expect_tx(fb, 2 * (C::kStageA + C::kStageB));
+          const uint32_t sa = ptx::smem_u32(smem_a + stage * C::kStageA);
+          const uint32_t sb = ptx::smem_u32(smem_b + stage * C::kStageB);
+          if (p.mode == 1) {
+            const int tap = kb / p.cin_blocks, cblk = kb - tap * p.cin_blocks;
+            const int dy = tap / 3, dx = tap - dy * 3;
+            ptx::tma2_load_4d(sa, &tmap_a, fb, cblk * BLOCK_K, cx0 + dx - 1, cy0 + dy - 1, cb);
+            ptx::tma2_load_3d(sb, &tmap_b, fb, cblk * BLOCK_K, tap, tn * BLOCK_N + int(cta_rank) * (BLOCK_N / 2));
+          } else {
+            ptx::tma2_load_2d(sa, &tmap_a, fb, kb * BLOCK_K, tm * BLOCK_M);
+            ptx::tma2_load_3d(sb, &tmap_b, fb, kb * BLOCK_K, 0, tn * BLOCK_N + int(cta_rank) * (BLOCK_N / 2));
+          }
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (pair leader only) =================
+    if (leader && ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        ptx::mbar_wait(ptx::smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
+          ptx::tc_fence_after();
+          const uint64_t da = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_a + stage * C::kStageA));
+          const uint64_t db = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_b + stage * C::kStageB));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 32 B (=UMMA_K bf16) inside the 128 B swizzle row: +2 in 16-byte units
+            ptx::umma2_bf16_ss(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma2_commit_mc(ptx::smem_u32(&empty_bar[stage]));
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma2_commit_mc(ptx::smem_u32(&tfull_bar[acc]));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue warps =================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int row_in_tile = quarter * 32 + lane;
+    // column split between the two warps of a quarter; the head tail needs whole rows -> first warp only
+    constexpr int kChunks = BLOCK_N / 32;
+    const int half = (warp - 2) >> 2;
+    const bool whole_row = (p.flags & F_HEAD_FINAL) != 0;
+    const int ch_begin = whole_row ? 0 : half * (kChunks / 2);
+    const int ch_end = whole_row ? (half == 0 ? kChunks : 0) : (half + 1) * (kChunks / 2);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t flags = p.flags;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      const int tn = tile % n_tiles, tm = (tile / n_tiles) * 2 + int(cta_rank);
+      // ---- where does this thread's row live in the output? ----
+      bool valid;
+      long long row_off;        // element offset of column 0 of this row in out (plain / conv)
+      int tok = 0;              // token index inside its image (RoPE)
+      long long pix = 0;        // output pixel index (head tail)
+      int ct_b = 0, ct_iy = 0, ct_ix = 0;
+      if (p.mode == 1) {
+        const int cb = tm / (p.tiles_y * p.tiles_x);
+        const int r = tm - cb * (p.tiles_y * p.tiles_x);
+        const int y = (r / p.tiles_x) * p.tile_h + row_in_tile / p.tile_w;
+        const int x = (r % p.tiles_x) * p.tile_w + row_in_tile % p.tile_w;
+        valid = (cb < p.cB) && (y < p.cH) && (x < p.cW);
+        pix = (long long)(cb * p.cH + y) * p.cW + x;
+        row_off = pix * p.ldo;
+      } else {
+        const int row = tm * BLOCK_M + row_in_tile;
+        valid = row < p.M;
+        row_off = (long long)row * p.ldo;
+        if (flags & F_ROPE) tok = row % p.tokens_per_img;
+        if (flags & F_CONVT) {
+          ct_b = row / (p.th_in * p.tw_in);
+          const int r = row - ct_b * (p.th_in * p.tw_in);
+          ct_iy = r / p.tw_in;
+          ct_ix = r - ct_iy * p.tw_in;
+        }
+      }
+      float head_acc[4] = {0.f, 0.f, 0.f, 0.f};
+
+      ptx::mbar_wait(ptx::smem_u32(&tfull_bar[acc]), acc_phase);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int ch = ch_begin; ch < ch_end; ++ch) {
+        const int col0 = tn * BLOCK_N + ch * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t raw[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BLOCK_N + ch * 32), raw);
+        ptx::tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+        if (flags & F_BIAS) {
+          const int bcol = (flags & F_CONVT) ? (col0 % p.tCout) : col0;
+          const float4* b4p = reinterpret_cast<const float4*>(p.bias + bcol);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4p + j);
+            v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          }
+        }
+        if (flags & F_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        }
+        if ((flags & F_ROPE) && col0 < p.rope_cols) {
+          // chunk = one half (y or x) of a 64-wide head: pairs (k, k+16), angle = pos * base^(-k/16)
+          const int pos = ((col0 & 63) < 32) ? (tok / p.grid_w) : (tok % p.grid_w);
+          const float4* c4 = reinterpret_cast<const float4*>(p.rope_cos + pos * 16);
+          const float4* s4 = reinterpret_cast<const float4*>(p.rope_sin + pos * 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 c = __ldg(c4 + j), s = __ldg(s4 + j);
+            const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float u = v[4 * j + t], w = v[4 * j + t + 16];
+              v[4 * j + t] = u * cc[t] - w * ss[t];
+              v[4 * j + t + 16] = w * cc[t] + u * ss[t];
+            }
+          }
+        }
+        if (flags & F_HEAD_FINAL) {
+          // relu(conv) . w4  accumulated across the 4 chunks of the 128-channel row
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float r = fmaxf(v[j], 0.f);
+            const int c = ch * 32 + j;
+            head_acc[0] += r * s_w4[0 * 128 + c];
+            head_acc[1] += r * s_w4[1 * 128 + c];
+            head_acc[2] += r * s_w4[2 * 128 + c];
+            head_acc[3] += r * s_w4[3 * 128 + c];
+          }
+          continue;
+        }
+        if (!valid) continue;
+        long long off;
+        if (flags & F_CONVT) {
+          const int kk = col0 / p.tCout, co = col0 - kk * p.tCout;
+          const int ky = kk / p.tk, kx = kk - ky * p.tk;
+          off = ((long long)(ct_b * p.th_in * p.tk + ct_iy * p.tk + ky) * (p.tw_in * p.tk) + ct_ix * p.tk + kx) * p.tCout + co;
+        } else {
+          off = row_off + col0;
+        }
+        if (flags & F_ADD0) {
+          const uint4* a = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.add0) + off);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 q = __ldg(a + j);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[t]);
+              v[8 * j + 2 * t] += __low2float(h);
+              v[8 * j + 2 * t + 1] += __high2float(h);
+            }
+          }
+        }
+        if (flags & F_ADD1) {
+          const uint4* a = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.add1) + off);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 q = __ldg(a + j);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[t]);
+              v[8 * j + 2 * t] += __low2float(h);
+              v[8 * j + 2 * t + 1] += __high2float(h);
+            }
+          }
+        }
+        if (flags & F_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (flags & (F_OUT_F32 | F_RESID_INPLACE)) {
+          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off);
+          if (flags & F_RESID_INPLACE) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 r = o[j];
+              v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          if (flags & F_OUT2_BF16) {
+            uint4* o2 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + off);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              o2[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                 pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+          }
+        } else {
+          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            o[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                              pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+          if (flags & F_OUT2_RELU) {
+            uint4* o2 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + off);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              o2[j] = make_uint4(pack_bf16(fmaxf(v[8 * j], 0.f), fmaxf(v[8 * j + 1], 0.f)),
+                                 pack_bf16(fmaxf(v[8 * j + 2], 0.f), fmaxf(v[8 * j + 3], 0.f)),
+                                 pack_bf16(fmaxf(v[8 * j + 4], 0.f), fmaxf(v[8 * j + 5], 0.f)),
+                                 pack_bf16(fmaxf(v[8 * j + 6], 0.f), fmaxf(v[8 * j + 7], 0.f)));
+          }
+        }
+      }
+      // accumulator drained: hand the TMEM buffer back to the MMA warp
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(ptx::smem_u32(&tempty_bar[acc]), 0);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+
+      if ((flags & F_HEAD_FINAL) && valid && half == 0) {
+        // dust3r/heads/postprocess.py: pts3d = xyz/|xyz| * f(|xyz|), conf = vmin + exp(x) (clipped)
+        const float x = head_acc[0] + s_w4[512 + 0], y = head_acc[1] + s_w4[512 + 1], z = head_acc[2] + s_w4[512 + 2];
+        float ox = x, oy = y, oz = z;
+        if (p.depth_mode != 0) {
+          const float d = sqrtf(x * x + y * y + z * z);
+          const float dc = fmaxf(d, 1e-8f);
+          const float s = (p.depth_mode == 2) ? expm1f(d) : d * d;
+          ox = x / dc * s; oy = y / dc * s; oz = z / dc * s;
+        }
+        float* o = p.pts3d + pix * 3;
+        o[0] = ox; o[1] = oy; o[2] = oz;
+        if (p.conf_mode != 0) {
+          const float c = head_acc[3] + s_w4[512 + 3];
+          float r;
+          if (p.conf_mode == 1) r = p.conf_min + fminf(expf(c), p.conf_max - p.conf_min);
+          else r = (p.conf_max - p.conf_min) * (1.f / (1.f + expf(-c))) + p.conf_min;
+          p.conf[pix] = r;
+        }
+      }
+    }
+  }
+
+  // ---- teardown ----
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc2(tmem_base, C::kTmemCols);
+  }
+}
+
+}  // namespace gemm
+}  // namespace d3r

@@ -1,5 +1,6 @@
 // Host side of the tcgen05 GEMM / conv kernels: tensor-map construction, tile-shape selection, launch.
 #include "gemm_tcgen05.cuh"
+#include "gemm2_tcgen05.cuh"
 #include "gemm_host.h"
 #include "prof.h"
 #include <mutex>
@@ -43,6 +44,8 @@ static int encode(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* d
   return D3R_OK;
 }
 
+bool use_pair(int bn);
+
 int pick_block_n(int N, uint32_t flags) {
   if (flags & F_HEAD_FINAL) return 128;
   if (N % 256 == 0) return 256;
@@ -67,7 +70,35 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
   return D3R_OK;
 }
 
+static int g_impl = 0;   // 0: 1-CTA kernels, 1: CTA-pair (cta_group::2) kernels for BLOCK_N >= 128
+void set_impl(int impl) { g_impl = impl; }
+bool use_pair(int bn) { return g_impl == 1 && bn >= 128; }
+
+template <int BN>
+static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int m_tiles, int n_tiles, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    D3R_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN>::kSmemBytes));
+    attr_set = true;
+  }
+  const int cluster_tiles = ((m_tiles + 1) / 2) * n_tiles;
+  const int max_clusters = num_sms() / 2;
+  const int clusters = cluster_tiles < max_clusters ? cluster_tiles : max_clusters;
+  const char* tag = (p.mode == 1) ? ((p.flags & F_HEAD_FINAL) ? "conv3x3_head_tail_2cta" : "conv3x3_tcgen05_2cta")
+                                  : (BN == 256 ? "gemm_tcgen05_2cta_bn256" : "gemm_tcgen05_2cta_bn128");
+  prof::Scope scope(tag, st, 2.0 * double(p.M) * double(p.N) * double(p.K));
+  gemm2_kernel<BN><<<2 * clusters, kNumThreads, Cfg2<BN>::kSmemBytes, st>>>(ta, tb, p);
+  D3R_LAUNCH_CHECK();
+  return D3R_OK;
+}
+
 static int dispatch(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int total_tiles, cudaStream_t st) {
+  if (use_pair(bn)) {
+    const int n_tiles = (p.N + bn - 1) / bn;
+    const int m_tiles = total_tiles / n_tiles;
+    if (bn == 256) return launch2<256>(ta, tb, p, m_tiles, n_tiles, st);
+    return launch2<128>(ta, tb, p, m_tiles, n_tiles, st);
+  }
   switch (bn) {
     case 256: return launch<256>(ta, tb, p, total_tiles, st);
     case 128: return launch<128>(ta, tb, p, total_tiles, st);
@@ -81,7 +112,7 @@ static int dispatch(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const 
 static int make_tmap_b(CUtensorMap* m, const void* B, int N, int taps, int Kc, int bn) {
   cuuint64_t dims[3] = {(cuuint64_t)Kc, (cuuint64_t)taps, (cuuint64_t)N};
   cuuint64_t str[2] = {(cuuint64_t)Kc * 2, (cuuint64_t)taps * Kc * 2};
-  cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, 1, (cuuint32_t)bn};
+  cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, 1, (cuuint32_t)(use_pair(bn) ? bn / 2 : bn)};   // each CTA of a pair stages half of B
   return encode(m, B, 3, dims, str, box);
 }
 
@@ -145,6 +176,8 @@ int conv3x3_bf16(const void* x_nhwc, const void* w_packed, int B, int H, int W, 
 
 // ---- building blocks exported through the C ABI (used by the unit tests and by forward.cu) ----
 using namespace d3r;
+
+extern "C" void d3r_set_gemm_impl(int32_t impl) { gemm::set_impl(impl); }
 
 extern "C" int d3r_gemm_bf16(const void* A, const void* B, void* out, const float* bias, const void* add0, void* out2,
                              int32_t M, int32_t N, int32_t K, int64_t ldo, uint32_t flags, const float* rope_cos,

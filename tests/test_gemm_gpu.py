@@ -14,6 +14,15 @@ from dust3r_b200._lib_fwd import (F_BIAS, F_GELU, F_RELU, F_OUT_F32, F_RESID_INP
                                   F_ROPE, F_OUT2_BF16)
 
 
+@pytest.fixture(params=[0, 1], ids=['cta1', 'cta_pair'], autouse=True)
+def gemm_impl(request):
+    """every test runs on both kernel families: 1-CTA tcgen05 and CTA-pair (cta_group::2)"""
+    lib = _lib.get_lib()
+    lib.d3r_set_gemm_impl(request.param)
+    yield request.param
+    lib.d3r_set_gemm_impl(0)
+
+
 def _p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
