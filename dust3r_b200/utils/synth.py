@@ -90,3 +90,43 @@ def synth_pair_predictions(n_imgs: int, edges, H: int, W: int, seed: int = 0):
     pred1 = dict(pts3d=pts1, conf=conf1)
     pred2 = dict(pts3d_in_other_view=pts2, conf=conf2)
     return dict(view1=view1, view2=view2, pred1=pred1, pred2=pred2, loss=None)
+
+
+def synth_consistent_scene(n_imgs: int, edges, H: int, W: int, seed: int = 0, noise: float = 0.01):
+    """A geometrically consistent toy scene: smooth random depth maps seen by cameras on a small arc, exact
+    pairwise pointmaps (image i's points in camera i's frame / image j's points in camera i's frame) plus
+    a little noise, confidences in [1.5, 6].  Gives the initialisers (MST / PnP / Procrustes) something
+    meaningful to recover, unlike synth_pair_predictions' white noise."""
+    import numpy as np
+    g = _gen(seed, f'scene{n_imgs}:{H}x{W}')
+    f = 1.2 * max(H, W)
+    vs, us = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing='ij')
+    cams, clouds = [], []
+    for i in range(n_imgs):
+        low = torch.rand((1, 1, 4, 4), generator=g)
+        depth = 2.0 + torch.nn.functional.interpolate(low, size=(H, W), mode='bicubic', align_corners=True)[0, 0]
+        pts_cam = torch.stack(((us - W / 2) * depth / f, (vs - H / 2) * depth / f, depth), dim=-1)
+        ang = 0.25 * (i - (n_imgs - 1) / 2)
+        R = torch.tensor([[math.cos(ang), 0, math.sin(ang)], [0, 1, 0], [-math.sin(ang), 0, math.cos(ang)]], dtype=torch.float32)
+        t = torch.tensor([1.5 * math.sin(ang), 0.05 * i, 0.3 * (1 - math.cos(ang))], dtype=torch.float32)
+        c2w = torch.eye(4)
+        c2w[:3, :3], c2w[:3, 3] = R, t
+        cams.append(c2w)
+        clouds.append(pts_cam)
+
+    def to_frame(pts_cam, c2w_src, c2w_dst):
+        world = pts_cam @ c2w_src[:3, :3].T + c2w_src[:3, 3]
+        w2c = torch.linalg.inv(c2w_dst)
+        return world @ w2c[:3, :3].T + w2c[:3, 3]
+    p1, p2, c1, c2 = [], [], [], []
+    for (i, j) in edges:
+        p1.append(clouds[i] + noise * torch.randn((H, W, 3), generator=g))
+        p2.append(to_frame(clouds[j], cams[j], cams[i]) + noise * torch.randn((H, W, 3), generator=g))
+        c1.append(1.5 + 4.5 * torch.rand((H, W), generator=g))
+        c2.append(1.5 + 4.5 * torch.rand((H, W), generator=g))
+    ts = torch.from_numpy(np.int32([[H, W]] * len(edges)))
+    out = dict(view1=dict(idx=[int(i) for i, j in edges], instance=[str(i) for i, j in edges], true_shape=ts),
+               view2=dict(idx=[int(j) for i, j in edges], instance=[str(j) for i, j in edges], true_shape=ts),
+               pred1=dict(pts3d=torch.stack(p1), conf=torch.stack(c1)),
+               pred2=dict(pts3d_in_other_view=torch.stack(p2), conf=torch.stack(c2)), loss=None)
+    return out, torch.stack(cams), f

@@ -1,0 +1,85 @@
+"""init='mst' host algorithm: CPU tests of the spanning-tree / Procrustes / PnP initialiser."""
+import copy
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, has_reference
+from dust3r_b200.utils.synth import synth_consistent_scene
+
+
+def _edges(n):
+    e = [(i, j) for i in range(n) for j in range(i)]
+    return e + [(j, i) for i, j in e]
+
+
+def test_mst_init_recovers_consistent_scene():
+    """On an exactly consistent scene the initialiser alone must nearly zero the objective's residuals: the
+    world pointmaps of every image agree with each aligned pairwise prediction."""
+    from dust3r_b200.cloud_opt import global_aligner
+    from dust3r_b200.cloud_opt import init_im_poses as init_fun
+    from dust3r_b200.utils.geometry import geotrf
+    n, H, W = 4, 24, 32
+    out, cams, f = synth_consistent_scene(n, _edges(n), H, W, seed=1, noise=0.0)
+    import cv2
+    cv2.setRNGSeed(0)
+    torch.manual_seed(0)
+    net = global_aligner(copy.deepcopy(out), 'cpu', verbose=False)
+    init_fun.minimum_spanning_tree  # noqa
+    pts3d, msp_edges, im_focals, im_poses = init_fun.minimum_spanning_tree(
+        net.imshapes, net.edges, net.pred_i, net.pred_j, net.conf_i, net.conf_j, net.im_conf, net.min_conf_thr, 'cpu',
+        has_im_poses=True, verbose=False)
+    assert len(msp_edges) == n - 1
+    assert all(abs(fo - f) / f < 0.05 for fo in im_focals)
+    # relative geometry: pairwise camera-centre distances match the ground truth up to one global scale
+    c_est = im_poses[:, :3, 3]
+    c_gt = cams[:, :3, 3]
+    d_est = torch.cdist(c_est, c_est)
+    d_gt = torch.cdist(c_gt, c_gt)
+    s = (d_est.sum() / d_gt.sum())
+    assert torch.allclose(d_est, s * d_gt, atol=0.05 * float(d_gt.max()) * float(s))
+
+
+@pytest.mark.skipif(not has_reference(), reason='reference not mounted')
+def test_mst_init_matches_reference():
+    """Same inputs, same cv2 RNG seed -> same initial parameters as the reference initialiser
+    (reference cloud_opt + local roma restatement)."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle', 'roma_stub'))
+    sys.path.insert(0, '/root/reference')
+    import cv2
+    from dust3r.cloud_opt import global_aligner as ref_aligner
+    import dust3r.cloud_opt.init_im_poses as ref_init
+    from dust3r_b200.cloud_opt import global_aligner
+    import dust3r_b200.cloud_opt.init_im_poses as init_fun
+    n, H, W = 4, 24, 32
+    out, cams, f = synth_consistent_scene(n, _edges(n), H, W, seed=2, noise=0.005)
+
+    torch.manual_seed(3)
+    cv2.setRNGSeed(0)
+    ref = ref_aligner(copy.deepcopy(out), 'cpu', verbose=False)
+    ref.verbose = False
+    ref_init.init_minimum_spanning_tree(ref, niter_PnP=10)
+
+    torch.manual_seed(3)
+    cv2.setRNGSeed(0)
+    net = global_aligner(copy.deepcopy(out), 'cpu', verbose=False)
+    pts3d, _, im_focals, im_poses = init_fun.minimum_spanning_tree(
+        net.imshapes, net.edges, net.pred_i, net.pred_j, net.conf_i, net.conf_j, net.im_conf, net.min_conf_thr, 'cpu',
+        has_im_poses=True, niter_PnP=10, verbose=False)
+    # init_from_pts3d ends with a loss evaluation, which needs the GPU kernel; set parameters only
+    net.verbose = False
+    try:
+        init_fun.init_from_pts3d(net, pts3d, im_focals, im_poses)
+    except Exception as e:  # pragma: no cover
+        raise
+    for k in ('pw_poses', 'im_poses', 'im_focals'):
+        a, b = getattr(ref, k).data, getattr(net, k).data
+        if k.endswith('poses'):   # quaternion sign is arbitrary
+            qa, qb = a[:, :4], b[:, :4]
+            sign = torch.sign((qa * qb).sum(-1, keepdim=True))
+            b = torch.cat((qb * sign, b[:, 4:]), dim=-1)
+        assert torch.allclose(a, b, atol=2e-3, rtol=2e-3), (k, float((a - b).abs().max()))
+    assert torch.allclose(ref.im_depthmaps.data, net.im_depthmaps.data, atol=2e-3, rtol=2e-3)
