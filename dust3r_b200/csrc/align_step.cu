@@ -601,18 +601,34 @@ align_iter_kernel(const __grid_constant__ d3r_align_desc D, int it) {
   __syncthreads();
   if (!s_flag) return;
   __threadfence();
-  for (int idx = tid; idx < deg * kEntVals; idx += kThreadsIter) {
-    const int k = idx / kEntVals, v = idx - k * kEntVals;
-    const float* src = ws.ent_part + int64_t(e0 + k) * D.max_chunks * kEntVals + v;
-    float s = 0.f;
-    for (int c = 0; c < nchunk_img; ++c) s += __ldcg(src + c * kEntVals);
-    __stcg(ws.ent_sum + (e0 + k) * kEntVals + v, s);
-  }
-  if (tid < kImgVals) {
-    const float* src = ws.img_part + int64_t(D.img_chunk_ptr[img]) * kImgVals + tid;
-    float s = 0.f;
-    for (int c = 0; c < nchunk_img; ++c) s += __ldcg(src + c * kImgVals);
-    __stcg(ws.img_sum + img * kImgVals + tid, s);
+  // one warp per (entry, value) row: lanes take chunks round-robin (independent loads in flight), then a fixed
+  // shuffle tree -> deterministic and ~100x shorter than a serial walk over the chunks
+  for (int task = warp; task < deg * kEntVals + kImgVals; task += kWarps) {
+    const float* src;
+    float* dst;
+    int stride;
+    if (task < deg * kEntVals) {
+      const int k = task / kEntVals, v = task - k * kEntVals;
+      src = ws.ent_part + int64_t(e0 + k) * D.max_chunks * kEntVals + v;
+      dst = ws.ent_sum + (e0 + k) * kEntVals + v;
+      stride = kEntVals;
+    } else {
+      const int v = task - deg * kEntVals;
+      src = ws.img_part + int64_t(D.img_chunk_ptr[img]) * kImgVals + v;
+      dst = ws.img_sum + img * kImgVals + v;
+      stride = kImgVals;
+    }
+    float sacc = 0.f;
+    for (int c0 = 0; c0 < nchunk_img; c0 += 128) {   // 4 independent loads per lane in flight
+      const int ca = c0 + lane, cb = ca + 32, cc = ca + 64, cd = ca + 96;
+      const float va = ca < nchunk_img ? __ldcg(src + ca * stride) : 0.f;
+      const float vb = cb < nchunk_img ? __ldcg(src + cb * stride) : 0.f;
+      const float vc = cc < nchunk_img ? __ldcg(src + cc * stride) : 0.f;
+      const float vd = cd < nchunk_img ? __ldcg(src + cd * stride) : 0.f;
+      sacc += (va + vb) + (vc + vd);
+    }
+    sacc = warp_sum(sacc);
+    if (lane == 0) __stcg(dst, sacc);
   }
   if (tid == 0) D.counters[img] = 0;  // re-arm for the next launch
 

@@ -344,6 +344,8 @@ int attention_hd64_tc(const void* q, long long ldq, const void* k, long long ldk
   static bool attr = false;
   if (!attr) {
     D3R_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+    // two CTAs per SM only fit with the maximum shared-memory carve-out
+    D3R_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr = true;
   }
   dim3 grid((Nq + tc::BQ - 1) / tc::BQ, heads, B);

@@ -44,7 +44,7 @@ static int encode(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* d
   return D3R_OK;
 }
 
-bool use_pair(int bn);
+bool use_pair(int bn, int num_kb);
 
 int pick_block_n(int N, uint32_t flags) {
   if (flags & F_HEAD_FINAL) return 128;
@@ -70,9 +70,13 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
   return D3R_OK;
 }
 
-static int g_impl = 0;   // 0: 1-CTA kernels, 1: CTA-pair (cta_group::2) kernels for BLOCK_N >= 128
+// 0: 1-CTA kernels, 1: CTA-pair (cta_group::2) kernels whenever BLOCK_N >= 128, 2 (default): pair kernels when
+// the mainloop dominates the tile (>= 32 k-blocks: fc2, the 3x3 convolutions), 1-CTA kernels otherwise (short-K
+// tiles are epilogue-bound and gain nothing from halving the operand traffic; measured in
+// profiles/r01_gemm_impl_compare.jsonl)
+static int g_impl = 2;
 void set_impl(int impl) { g_impl = impl; }
-bool use_pair(int bn) { return g_impl == 1 && bn >= 128; }
+bool use_pair(int bn, int num_kb) { return bn >= 128 && (g_impl == 1 || (g_impl == 2 && num_kb >= 32)); }
 
 template <int BN>
 static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int m_tiles, int n_tiles, cudaStream_t st) {
@@ -93,7 +97,7 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p
 }
 
 static int dispatch(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int total_tiles, cudaStream_t st) {
-  if (use_pair(bn)) {
+  if (use_pair(bn, p.num_kb)) {
     const int n_tiles = (p.N + bn - 1) / bn;
     const int m_tiles = total_tiles / n_tiles;
     if (bn == 256) return launch2<256>(ta, tb, p, m_tiles, n_tiles, st);
@@ -109,10 +113,10 @@ static int dispatch(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const 
 }
 
 // B operand: [N][taps][Kc] bf16, K-major
-static int make_tmap_b(CUtensorMap* m, const void* B, int N, int taps, int Kc, int bn) {
+static int make_tmap_b(CUtensorMap* m, const void* B, int N, int taps, int Kc, int bn, int num_kb) {
   cuuint64_t dims[3] = {(cuuint64_t)Kc, (cuuint64_t)taps, (cuuint64_t)N};
   cuuint64_t str[2] = {(cuuint64_t)Kc * 2, (cuuint64_t)taps * Kc * 2};
-  cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, 1, (cuuint32_t)(use_pair(bn) ? bn / 2 : bn)};   // each CTA of a pair stages half of B
+  cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, 1, (cuuint32_t)(use_pair(bn, num_kb) ? bn / 2 : bn)};   // each CTA of a pair stages half of B
   return encode(m, B, 3, dims, str, box);
 }
 
@@ -133,7 +137,7 @@ int gemm_bf16(const void* A, long long lda, const void* B, Params p, cudaStream_
     int rc = encode(&ta, A, 2, dims, str, box);
     if (rc) return rc;
   }
-  int rc = make_tmap_b(&tb, B, p.N, 1, p.K, bn);
+  int rc = make_tmap_b(&tb, B, p.N, 1, p.K, bn, p.num_kb);
   if (rc) return rc;
   const int total = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + bn - 1) / bn);
   return dispatch(bn, ta, tb, p, total, st);
@@ -165,7 +169,7 @@ int conv3x3_bf16(const void* x_nhwc, const void* w_packed, int B, int H, int W, 
     int rc = encode(&ta, x_nhwc, 4, dims, str, box);
     if (rc) return rc;
   }
-  int rc = make_tmap_b(&tb, w_packed, Cout, 9, Cin, bn);
+  int rc = make_tmap_b(&tb, w_packed, Cout, 9, Cin, bn, p.num_kb);
   if (rc) return rc;
   const int total = B * p.tiles_x * p.tiles_y * ((p.N + bn - 1) / bn);
   return dispatch(bn, ta, tb, p, total, st);

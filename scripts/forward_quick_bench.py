@@ -45,5 +45,9 @@ def forward(Bp):
         packed._ws = None; packed._ws_key = None
 
 if __name__ == '__main__':
-    gemm_shapes()
-    forward([1, 8, 32])
+    lib = _lib.get_lib()
+    for impl in (0, 2):
+        lib.d3r_set_gemm_impl(impl)
+        print(json.dumps(dict(kind='gemm_impl', impl=impl)), flush=True)
+        gemm_shapes()
+        forward([8, 32])

@@ -20,7 +20,7 @@ def gemm_impl(request):
     lib = _lib.get_lib()
     lib.d3r_set_gemm_impl(request.param)
     yield request.param
-    lib.d3r_set_gemm_impl(0)
+    lib.d3r_set_gemm_impl(2)
 
 
 def _p(t):
