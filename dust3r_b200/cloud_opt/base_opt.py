@@ -304,6 +304,7 @@ def global_alignment_loop(net, lr=0.01, niter=300, schedule='cosine', lr_min=1e-
     if niter <= 0:
         return float('inf')
     loss = float(losses[-1])  # the only host sync of the loop
+    eng.check_overflow()
     if net.verbose:
         print(f' final loss={loss:g} after {niter} iterations')
     return loss

@@ -267,6 +267,15 @@ class AlignEngine:
         _lib.check(self.lib.d3r_align_run(C.byref(d), 0, niter, _lib.stream_ptr()))
         return self.loss_out
 
+    def check_overflow(self):
+        """Raises if a fixed-point accumulator left its range (host sync)."""
+        flag = C.c_int32(0)
+        d = self._desc()
+        _lib.check(self.lib.d3r_align_overflow_flag(C.byref(d), C.byref(flag), _lib.stream_ptr()))
+        if flag.value:
+            raise _lib.D3RError('alignment: a gradient partial sum exceeded the fixed-point accumulator range (|x| >= 2^18); '
+                                'rescale the scene (pointmaps are expected in metric-like units)')
+
     def evaluate_loss(self):
         """net.forward(): the objective at the current parameters, nothing updated."""
         self.sched = torch.zeros((1, 4), dtype=torch.float32, device=self.device)

@@ -33,32 +33,47 @@ constexpr int kEdgeT = 12;                 // M = s*R*diag(adapt) (9) + s*T (3)
 constexpr int kImgT = 16;                  // R (9) T (3) 1/fx 1/fy cx cy
 
 struct Workspace {
-  float* edgeT;     // [E][12]
-  float* imgT;      // [n][16]
-  float* ent_part;  // [2E][max_chunks][13]
-  float* img_part;  // [n_chunks][12]
-  float* ent_sum;   // [2E][13]
-  float* img_sum;   // [n][12]
+  float* edgeT;          // [E][12]
+  float* imgT;           // [n][16]
+  long long* ent_acc;    // [2E][13]  fixed-point (2^44) accumulators, zero between launches
+  long long* img_acc;    // [n][12]
+  float* g_edge;         // [E][10]   small-step scratch: pairwise-pose / adaptor gradients
+  float* g_img;          // [n][11]   pose (7) / focal (2) / pp (2) gradients
+  int* flags;            // [4]       [0] = fixed-point overflow seen
 };
 
 __host__ __device__ inline int64_t align4(int64_t x) { return (x + 3) & ~int64_t(3); }
 
-__host__ __device__ inline Workspace carve(float* ws, int n, int E, int n_chunks, int max_chunks) {
+__host__ __device__ inline Workspace carve(float* ws, int n, int E) {
   Workspace w;
   int64_t o = 0;
   w.edgeT = ws + o;    o += align4(int64_t(E) * kEdgeT);
   w.imgT = ws + o;     o += align4(int64_t(n) * kImgT);
-  w.ent_part = ws + o; o += align4(int64_t(2) * E * max_chunks * kEntVals);
-  w.img_part = ws + o; o += align4(int64_t(n_chunks) * kImgVals);
-  w.ent_sum = ws + o;  o += align4(int64_t(2) * E * kEntVals);
-  w.img_sum = ws + o;  o += align4(int64_t(n) * kImgVals);
+  w.ent_acc = reinterpret_cast<long long*>(ws + o); o += align4(int64_t(2) * E * kEntVals * 2);
+  w.img_acc = reinterpret_cast<long long*>(ws + o); o += align4(int64_t(n) * kImgVals * 2);
+  w.g_edge = ws + o;   o += align4(int64_t(E) * 10);
+  w.g_img = ws + o;    o += align4(int64_t(n) * 11);
+  w.flags = reinterpret_cast<int*>(ws + o); o += 4;
   return w;
 }
 
-inline int64_t workspace_floats(int n, int E, int n_chunks, int max_chunks) {
-  return align4(int64_t(E) * kEdgeT) + align4(int64_t(n) * kImgT) +
-         align4(int64_t(2) * E * max_chunks * kEntVals) + align4(int64_t(n_chunks) * kImgVals) +
-         align4(int64_t(2) * E * kEntVals) + align4(int64_t(n) * kImgVals);
+inline int64_t workspace_floats(int n, int E) {
+  return align4(int64_t(E) * kEdgeT) + align4(int64_t(n) * kImgT) + align4(int64_t(2) * E * kEntVals * 2) +
+         align4(int64_t(n) * kImgVals * 2) + align4(int64_t(E) * 10) + align4(int64_t(n) * 11) + 4;
+}
+
+// Order-independent (hence deterministic) cross-CTA accumulation: every CTA contributes its exactly-ordered fp32
+// partial sum as a 2^44 fixed-point integer through a 64-bit integer atomic.  Resolution 5.7e-14, range +-5e5.
+constexpr double kFixScale = 17592186044416.0;        // 2^44
+constexpr double kFixInv = 1.0 / 17592186044416.0;
+__device__ __forceinline__ void fix_add(long long* dst, float x, int* overflow_flag) {
+  if (!(fabsf(x) < 262144.f)) *overflow_flag = 1;     // also catches NaN / Inf
+  const long long q = __double2ll_rn(double(x) * kFixScale);
+  atomicAdd(reinterpret_cast<unsigned long long*>(dst), static_cast<unsigned long long>(q));
+}
+__device__ __forceinline__ float fix_get(const long long* src) {
+  const long long q = __ldcg(src);
+  return float(double(q) * kFixInv);
 }
 
 // offsets inside the `small` parameter buffer
@@ -105,242 +120,250 @@ __device__ __forceinline__ float adam_update(float p, float g, float& m, float& 
   return p - step_size * (m / denom);
 }
 
-// ---- derived transforms (run by one CTA) -------------------------------------------------------
+// optional timeline instrumentation (debug aid): 4 x uint64 globaltimer stamps per CTA
+__device__ unsigned long long* g_align_dbg = nullptr;
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+#define D3R_TSTAMP(i) do { if (g_align_dbg && threadIdx.x == 0) g_align_dbg[4 * size_t(D.n_chunks) + (i)] = gtime(); } while (0)
+
+// ---- derived transforms / small-parameter step (run by ONE CTA while the rest of the chip idles) ----------
+// Written for latency: independent global loads are issued together, block reductions cost one barrier (every
+// thread re-adds the 8 warp partials itself), pointers are __restrict__, and the edge work (low thread ids)
+// and image work (high thread ids) run concurrently on different warps.
+__device__ __forceinline__ float block_sum8(float v, float* slot /* 8 floats */) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) slot[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) t += slot[w];
+  return t;
+}
+
+struct EdgeGeom {
+  float R[9], T[3], ad[3], s, qh[4], qn;
+};
+__device__ __forceinline__ void edge_geom(const float* p8, float a0, float a1, const d3r_align_desc& D, float mean_sigma,
+                                          float log_base, EdgeGeom& g) {
+  quat_to_R(p8, g.R, g.qh, &g.qn);
+  g.s = expf(p8[7]);
+  if (D.norm_pw_scale) g.s *= expf(log_base - mean_sigma);
+  g.ad[0] = a0; g.ad[1] = a0; g.ad[2] = a1;
+  if (D.norm_pw_scale) {
+    const float mu = (a0 + a0 + a1) / 3.f;
+    g.ad[0] -= mu; g.ad[1] -= mu; g.ad[2] -= mu;
+  }
+#pragma unroll
+  for (int b = 0; b < 3; ++b) g.ad[b] = expf(g.ad[b] / D.pw_break);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) g.T[a] = signed_expm1f(p8[4 + a]);
+}
+
+// image i is handled by thread (blockDim-1-i) so that images and edges land on different warps
+__device__ __forceinline__ int img_of_thread(int it) { return int(blockDim.x) - 1 - int(threadIdx.x) + it * int(blockDim.x); }
+
 __device__ void compute_transforms(const d3r_align_desc& D, const Workspace& ws, float* s_red) {
   const int n = D.n_imgs, E = D.n_edges;
   const SmallLayout L(n, E);
-  const float* sm = D.small;
-  // mean of the pairwise log-scales (base_opt.py:178-184)
+  const float* __restrict__ sm = D.small;
   float part = 0.f;
   for (int e = threadIdx.x; e < E; e += blockDim.x) part += sm[L.pw + e * 8 + 7];
-  part = warp_sum(part);
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
-    s_red[32] = t / float(E);
-  }
-  __syncthreads();
-  const float mean_sigma = s_red[32];
+  const float mean_sigma = block_sum8(part, s_red) / float(E);   // base_opt.py:178-184
   const float log_base = logf(D.base_scale);
   for (int e = threadIdx.x; e < E; e += blockDim.x) {
-    const float* p = sm + L.pw + e * 8;
-    float R[9];
-    quat_to_R(p, R, nullptr, nullptr);
-    float s = expf(p[7]);
-    if (D.norm_pw_scale) s = s * expf(log_base - mean_sigma);
-    float a0 = sm[L.adapt + e * 2 + 0], a1 = sm[L.adapt + e * 2 + 1];
-    float ad[3] = {a0, a0, a1};
-    if (D.norm_pw_scale) {
-      float mu = (a0 + a0 + a1) / 3.f;
-      ad[0] -= mu; ad[1] -= mu; ad[2] -= mu;
-    }
-    for (int b = 0; b < 3; ++b) ad[b] = expf(ad[b] / D.pw_break);
+    float p8[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) p8[k] = sm[L.pw + e * 8 + k];
+    const float a0 = sm[L.adapt + e * 2 + 0], a1 = sm[L.adapt + e * 2 + 1];
+    EdgeGeom g;
+    edge_geom(p8, a0, a1, D, mean_sigma, log_base, g);
     float* o = ws.edgeT + e * kEdgeT;
+#pragma unroll
     for (int a = 0; a < 3; ++a)
-      for (int b = 0; b < 3; ++b) o[a * 3 + b] = s * R[a * 3 + b] * ad[b];
-    for (int a = 0; a < 3; ++a) o[9 + a] = s * signed_expm1f(p[4 + a]);
+#pragma unroll
+      for (int b = 0; b < 3; ++b) o[a * 3 + b] = g.s * g.R[a * 3 + b] * g.ad[b];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) o[9 + a] = g.s * g.T[a];
   }
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float* p = sm + L.poses + i * 7;
+  for (int r = 0, i = img_of_thread(0); i < n; i = img_of_thread(++r)) {
+    float p7[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) p7[k] = sm[L.poses + i * 7 + k];
+    const float f0 = sm[L.focals + i * 2 + 0], f1 = sm[L.focals + i * 2 + 1];
+    const float pp0 = sm[L.pp + i * 2 + 0], pp1 = sm[L.pp + i * 2 + 1];
+    const int Hh = D.img_hw[i * 2 + 0], Ww = D.img_hw[i * 2 + 1];
     float* o = ws.imgT + i * kImgT;
-    quat_to_R(p, o, nullptr, nullptr);
-    for (int a = 0; a < 3; ++a) o[9 + a] = signed_expm1f(p[4 + a]);
-    float fx = expf(sm[L.focals + i * 2 + 0] / D.focal_break);
-    float fy = expf(sm[L.focals + i * 2 + 1] / D.focal_break);
-    o[12] = 1.f / fx;
-    o[13] = 1.f / fy;
-    o[14] = 0.5f * float(D.img_hw[i * 2 + 1]) + 10.f * sm[L.pp + i * 2 + 0];
-    o[15] = 0.5f * float(D.img_hw[i * 2 + 0]) + 10.f * sm[L.pp + i * 2 + 1];
+    quat_to_R(p7, o, nullptr, nullptr);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) o[9 + a] = signed_expm1f(p7[4 + a]);
+    o[12] = 1.f / expf(f0 / D.focal_break);
+    o[13] = 1.f / expf(f1 / D.focal_break);
+    o[14] = 0.5f * float(Ww) + 10.f * pp0;
+    o[15] = 0.5f * float(Hh) + 10.f * pp1;
   }
 }
 
 __global__ void __launch_bounds__(kThreads) prepare_kernel(const __grid_constant__ d3r_align_desc D) {
   __shared__ float s_red[40];
-  Workspace ws = carve(D.workspace, D.n_imgs, D.n_edges, D.n_chunks, D.max_chunks);
+  Workspace ws = carve(D.workspace, D.n_imgs, D.n_edges);
   compute_transforms(D, ws, s_red);
 }
 
-// ---- small-parameter backward + Adam (run by the last CTA of the grid) -------------------------
+// backward through the small parameters + Adam; run by the last CTA of the grid
 __device__ void small_param_step(const d3r_align_desc& D, const Workspace& ws, int it, float* s_red) {
   const int n = D.n_imgs, E = D.n_edges;
   const SmallLayout L(n, E);
-  float* sm = D.small;
-  float* am = D.small_m;
-  float* av = D.small_v;
-  const uint8_t* tr = D.small_trainable;
+  float* __restrict__ sm = D.small;
+  float* __restrict__ am = D.small_m;
+  float* __restrict__ av = D.small_v;
+  const uint8_t* __restrict__ tr = D.small_trainable;
   const float step_size = D.sched[it * 4 + 1], bc2s = D.sched[it * 4 + 2];
   const float b1 = D.beta1, b2 = D.beta2, eps = D.adam_eps;
 
-  // loss = sum over entries (coefficients already folded in), fixed order
-  float lpart = 0.f;
-  for (int k = threadIdx.x; k < 2 * E; k += blockDim.x) lpart += __ldcg(ws.ent_sum + k * kEntVals + 12);
+  // phase 0: loss (fixed order over entries) and mean log-scale, one barrier
+  float lpart = 0.f, spart = 0.f;
+  for (int k = threadIdx.x; k < 2 * E; k += blockDim.x) lpart += fix_get(ws.ent_acc + k * kEntVals + 12);
+  for (int e = threadIdx.x; e < E; e += blockDim.x) spart += sm[L.pw + e * 8 + 7];
   lpart = warp_sum(lpart);
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = lpart;
+  spart = warp_sum(spart);
+  if ((threadIdx.x & 31) == 0) { s_red[threadIdx.x >> 5] = lpart; s_red[8 + (threadIdx.x >> 5)] = spart; }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
-    D.loss_out[it] = t;
-  }
-  __syncthreads();
-  if (D.eval_only) return;
-
-  // pass 1 over edges: dL/ds_e * s_e summed (the mean-coupling term of get_pw_norm_scale_factor)
-  float mean_sigma = 0.f;
-  {
-    float part = 0.f;
-    for (int e = threadIdx.x; e < E; e += blockDim.x) part += sm[L.pw + e * 8 + 7];
-    part = warp_sum(part);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float t = 0.f;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
-      s_red[32] = t / float(E);
-    }
-    __syncthreads();
-    mean_sigma = s_red[32];
-    __syncthreads();
-  }
+  float loss = 0.f, mean_sigma = 0.f;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) { loss += s_red[w]; mean_sigma += s_red[8 + w]; }
+  mean_sigma /= float(E);
+  if (threadIdx.x == 0) D.loss_out[it] = loss;
   const float log_base = logf(D.base_scale);
+  D3R_TSTAMP(0);
 
-  // per-edge gradient of (sigma_e) before the coupling, kept in registers across the two passes
-  // (each thread revisits the same edges in the same order)
+  // phase 1: gradients -> scratch.  edges on low thread ids, images on high thread ids (different warps).
   float coupl = 0.f;
-  for (int e = threadIdx.x; e < E; e += blockDim.x) {
-    const float* p = sm + L.pw + e * 8;
-    float R[9];
-    quat_to_R(p, R, nullptr, nullptr);
-    float s = expf(p[7]);
-    if (D.norm_pw_scale) s = s * expf(log_base - mean_sigma);
-    float a0 = sm[L.adapt + e * 2 + 0], a1 = sm[L.adapt + e * 2 + 1];
-    float ad[3] = {a0, a0, a1};
-    if (D.norm_pw_scale) { float mu = (a0 + a0 + a1) / 3.f; ad[0] -= mu; ad[1] -= mu; ad[2] -= mu; }
-    for (int b = 0; b < 3; ++b) ad[b] = expf(ad[b] / D.pw_break);
-    const float* si = ws.ent_sum + D.edge_ent[e * 2 + 0] * kEntVals;
-    const float* sj = ws.ent_sum + D.edge_ent[e * 2 + 1] * kEntVals;
-    float T[3];
-    for (int a = 0; a < 3; ++a) T[a] = signed_expm1f(p[4 + a]);
-    // dL/dM_ab = -sum g_a q_b ; dL/dt'_a = -sum g_a
-    float dLds = 0.f;
-    for (int a = 0; a < 3; ++a) {
-      for (int b = 0; b < 3; ++b) dLds -= (__ldcg(si + a * 3 + b) + __ldcg(sj + a * 3 + b)) * R[a * 3 + b] * ad[b];
-      dLds -= (__ldcg(si + 9 + a) + __ldcg(sj + 9 + a)) * T[a];
-    }
-    coupl += dLds * s;
-  }
-  coupl = warp_sum(coupl);
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = coupl;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
-    s_red[33] = t / float(E);
-  }
-  __syncthreads();
-  const float coupling = D.norm_pw_scale ? s_red[33] : 0.f;
-
-  for (int e = threadIdx.x; e < E; e += blockDim.x) {
-    float* p = sm + L.pw + e * 8;
-    float R[9], qh[4], qn;
-    quat_to_R(p, R, qh, &qn);
-    float s = expf(p[7]);
-    if (D.norm_pw_scale) s = s * expf(log_base - mean_sigma);
-    float a0 = sm[L.adapt + e * 2 + 0], a1 = sm[L.adapt + e * 2 + 1];
-    float ad[3] = {a0, a0, a1};
-    if (D.norm_pw_scale) { float mu = (a0 + a0 + a1) / 3.f; ad[0] -= mu; ad[1] -= mu; ad[2] -= mu; }
-    for (int b = 0; b < 3; ++b) ad[b] = expf(ad[b] / D.pw_break);
-    const float* si = ws.ent_sum + D.edge_ent[e * 2 + 0] * kEntVals;
-    const float* sj = ws.ent_sum + D.edge_ent[e * 2 + 1] * kEntVals;
-    float dM[9], dt[3], T[3];
-    for (int k = 0; k < 9; ++k) dM[k] = -(__ldcg(si + k) + __ldcg(sj + k));
-    for (int a = 0; a < 3; ++a) { dt[a] = -(__ldcg(si + 9 + a) + __ldcg(sj + 9 + a)); T[a] = signed_expm1f(p[4 + a]); }
-    float dLds = 0.f, dR[9], dad[3] = {0.f, 0.f, 0.f};
-    for (int a = 0; a < 3; ++a) {
-      for (int b = 0; b < 3; ++b) {
-        dLds += dM[a * 3 + b] * R[a * 3 + b] * ad[b];
-        dR[a * 3 + b] = dM[a * 3 + b] * s * ad[b];
-        dad[b] += dM[a * 3 + b] * s * R[a * 3 + b];
+  if (!D.eval_only) {
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+      float p8[8], si[12], sj[12];
+      const int ei = D.edge_ent[e * 2 + 0], ej = D.edge_ent[e * 2 + 1];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) p8[k] = sm[L.pw + e * 8 + k];
+      const float a0 = sm[L.adapt + e * 2 + 0], a1 = sm[L.adapt + e * 2 + 1];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) { si[k] = fix_get(ws.ent_acc + ei * kEntVals + k); sj[k] = fix_get(ws.ent_acc + ej * kEntVals + k); }
+      EdgeGeom g;
+      edge_geom(p8, a0, a1, D, mean_sigma, log_base, g);
+      float dM[9], dt[3];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) dM[k] = -(si[k] + sj[k]);   // dL/dM_ab = -sum g_a q_b
+#pragma unroll
+      for (int a = 0; a < 3; ++a) dt[a] = -(si[9 + a] + sj[9 + a]);
+      float dLds = 0.f, dR[9], dad[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          dLds += dM[a * 3 + b] * g.R[a * 3 + b] * g.ad[b];
+          dR[a * 3 + b] = dM[a * 3 + b] * g.s * g.ad[b];
+          dad[b] += dM[a * 3 + b] * g.s * g.R[a * 3 + b];
+        }
+        dLds += dt[a] * g.T[a];
       }
-      dLds += dt[a] * T[a];
+      float gr[10];
+      quat_backward(dR, g.qh, g.qn, gr);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float t = p8[4 + a];
+        const float sg = (t > 0.f) - (t < 0.f);
+        gr[4 + a] = dt[a] * g.s * sg * sg * expf(fabsf(t));
+      }
+      gr[7] = dLds * g.s;             // the mean-coupling term is subtracted in phase 2
+      coupl += dLds * g.s;
+      // adaptors (base_opt.py:143-148): adapt3 = exp((cat(a0,a0,a1) - mean)/pw_break)
+      float gad[3];
+#pragma unroll
+      for (int b = 0; b < 3; ++b) gad[b] = dad[b] * g.ad[b] / D.pw_break;
+      if (D.norm_pw_scale) { const float mu = (gad[0] + gad[1] + gad[2]) / 3.f; gad[0] -= mu; gad[1] -= mu; gad[2] -= mu; }
+      gr[8] = gad[0] + gad[1];
+      gr[9] = gad[2];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) ws.g_edge[e * 10 + k] = gr[k];
     }
-    float g[8];
-    quat_backward(dR, qh, qn, g);
-    for (int a = 0; a < 3; ++a) {
-      float t = p[4 + a];
-      float sg = (t > 0.f) - (t < 0.f);
-      g[4 + a] = dt[a] * s * sg * sg * expf(fabsf(t));
-    }
-    g[7] = dLds * s - coupling;
-    // adaptors (base_opt.py:143-148): adapt3 = exp((cat(a0,a0,a1) - mean)/pw_break)
-    float gad[3];
-    for (int b = 0; b < 3; ++b) gad[b] = dad[b] * ad[b] / D.pw_break;
-    if (D.norm_pw_scale) { float mu = (gad[0] + gad[1] + gad[2]) / 3.f; gad[0] -= mu; gad[1] -= mu; gad[2] -= mu; }
-    float ga[2] = {gad[0] + gad[1], gad[2]};
-    for (int k = 0; k < 8; ++k) {
-      int idx = L.pw + e * 8 + k;
-      if (tr[idx]) sm[idx] = adam_update(sm[idx], g[k], am[idx], av[idx], b1, b2, step_size, bc2s, eps);
-    }
-    for (int k = 0; k < 2; ++k) {
-      int idx = L.adapt + e * 2 + k;
-      if (tr[idx]) sm[idx] = adam_update(sm[idx], ga[k], am[idx], av[idx], b1, b2, step_size, bc2s, eps);
+    for (int r = 0, i = img_of_thread(0); i < n; i = img_of_thread(++r)) {
+      float q7[7], S[12];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) q7[k] = sm[L.poses + i * 7 + k];
+      const float f0 = sm[L.focals + i * 2 + 0], f1 = sm[L.focals + i * 2 + 1];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) S[k] = fix_get(ws.img_acc + i * kImgVals + k);   // S[a*3+b] = sum G_a c_b ; S[9+a] = sum G_a
+      float R[9], qh[4], qn;
+      quat_to_R(q7, R, qh, &qn);
+      float gr[11];
+      quat_backward(S, qh, qn, gr);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float t = q7[4 + a];
+        const float sg = (t > 0.f) - (t < 0.f);
+        gr[4 + a] = S[9 + a] * sg * sg * expf(fabsf(t));
+      }
+      // focals: c_x = d (u-cx)/fx, fx = exp(phi/focal_break);  pp: cx = W/2 + 10 pp_x
+      float gfx = 0.f, gfy = 0.f, gpx = 0.f, gpy = 0.f;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        gfx += R[a * 3 + 0] * S[a * 3 + 0];
+        gfy += R[a * 3 + 1] * S[a * 3 + 1];
+        gpx += R[a * 3 + 0] * S[a * 3 + 2];
+        gpy += R[a * 3 + 1] * S[a * 3 + 2];
+      }
+      gfx = -gfx / D.focal_break;
+      gfy = -gfy / D.focal_break;
+      // one shared focal: both slots get the summed gradient and evolve identically
+      gr[7] = D.tied_focal ? gfx + gfy : gfx;
+      gr[8] = D.tied_focal ? gfx + gfy : gfy;
+      gr[9] = -10.f * gpx / expf(f0 / D.focal_break);
+      gr[10] = -10.f * gpy / expf(f1 / D.focal_break);
+#pragma unroll
+      for (int k = 0; k < 11; ++k) ws.g_img[i * 11 + k] = gr[k];
     }
   }
+  D3R_TSTAMP(1);
+  // zero the accumulators for the next launch (everything has been read above; barrier inside block_sum8)
+  const float coupling = block_sum8(coupl, s_red + 16) / float(E);
+  for (int k = threadIdx.x; k < 2 * E * kEntVals; k += blockDim.x) ws.ent_acc[k] = 0;
+  for (int k = threadIdx.x; k < n * kImgVals; k += blockDim.x) ws.img_acc[k] = 0;
+  if (D.eval_only) return;
+  D3R_TSTAMP(2);
 
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    float* p = sm + L.poses + i * 7;
-    float R[9], qh[4], qn;
-    quat_to_R(p, R, qh, &qn);
-    const float* S = ws.img_sum + i * kImgVals;  // S[a*3+b] = sum G_a c_b ; S[9+a] = sum G_a
-    float dR[9];
-    for (int k = 0; k < 9; ++k) dR[k] = __ldcg(S + k);
-    float g[7];
-    quat_backward(dR, qh, qn, g);
-    for (int a = 0; a < 3; ++a) {
-      float t = p[4 + a];
-      float sg = (t > 0.f) - (t < 0.f);
-      g[4 + a] = __ldcg(S + 9 + a) * sg * sg * expf(fabsf(t));
-    }
-    for (int k = 0; k < 7; ++k) {
-      int idx = L.poses + i * 7 + k;
-      if (tr[idx]) sm[idx] = adam_update(sm[idx], g[k], am[idx], av[idx], b1, b2, step_size, bc2s, eps);
-    }
-    // focals: c_x = d (u-cx)/fx, fx = exp(phi/focal_break)
-    float gfx = 0.f, gfy = 0.f, gpx = 0.f, gpy = 0.f;
-    for (int a = 0; a < 3; ++a) {
-      gfx += R[a * 3 + 0] * dR[a * 3 + 0];
-      gfy += R[a * 3 + 1] * dR[a * 3 + 1];
-      gpx += R[a * 3 + 0] * dR[a * 3 + 2];
-      gpy += R[a * 3 + 1] * dR[a * 3 + 2];
-    }
-    gfx = -gfx / D.focal_break;
-    gfy = -gfy / D.focal_break;
-    float fx = expf(sm[L.focals + i * 2 + 0] / D.focal_break);
-    float fy = expf(sm[L.focals + i * 2 + 1] / D.focal_break);
-    gpx = -10.f * gpx / fx;
-    gpy = -10.f * gpy / fy;
-    if (D.tied_focal) {
-      int idx = L.focals + i * 2;
-      if (tr[idx]) {
-        float v = adam_update(sm[idx], gfx + gfy, am[idx], av[idx], b1, b2, step_size, bc2s, eps);
-        sm[idx] = v; sm[idx + 1] = v;
-      }
+  // phase 2: Adam over the flat parameter vector  [poses 7n | focals 2n | pp 2n | pw 8E | adapt 2E]
+  for (int idx = threadIdx.x; idx < L.total; idx += blockDim.x) {
+    if (!tr[idx]) continue;
+    float g;
+    if (idx < L.focals) {
+      const int i = idx / 7;
+      g = ws.g_img[i * 11 + (idx - i * 7)];
+    } else if (idx < L.pp) {
+      const int r = idx - L.focals;
+      g = ws.g_img[(r >> 1) * 11 + 7 + (r & 1)];
+    } else if (idx < L.pw) {
+      const int r = idx - L.pp;
+      g = ws.g_img[(r >> 1) * 11 + 9 + (r & 1)];
+    } else if (idx < L.adapt) {
+      const int r = idx - L.pw;
+      g = ws.g_edge[(r >> 3) * 10 + (r & 7)];
+      if ((r & 7) == 7 && D.norm_pw_scale) g -= coupling;
     } else {
-      int idx = L.focals + i * 2;
-      if (tr[idx]) sm[idx] = adam_update(sm[idx], gfx, am[idx], av[idx], b1, b2, step_size, bc2s, eps);
-      if (tr[idx + 1]) sm[idx + 1] = adam_update(sm[idx + 1], gfy, am[idx + 1], av[idx + 1], b1, b2, step_size, bc2s, eps);
+      const int r = idx - L.adapt;
+      g = ws.g_edge[(r >> 1) * 10 + 8 + (r & 1)];
     }
-    {
-      int idx = L.pp + i * 2;
-      if (tr[idx]) sm[idx] = adam_update(sm[idx], gpx, am[idx], av[idx], b1, b2, step_size, bc2s, eps);
-      if (tr[idx + 1]) sm[idx + 1] = adam_update(sm[idx + 1], gpy, am[idx + 1], av[idx + 1], b1, b2, step_size, bc2s, eps);
-    }
+    float m = am[idx], v = av[idx];
+    sm[idx] = adam_update(sm[idx], g, m, v, b1, b2, step_size, bc2s, eps);
+    am[idx] = m;
+    av[idx] = v;
   }
-  __threadfence_block();
+  D3R_TSTAMP(3);
   __syncthreads();
-  compute_transforms(D, ws, s_red);
+  compute_transforms(D, ws, s_red + 24);
+  D3R_TSTAMP(4);
 }
 
 // ---- the per-iteration kernel ---------------------------------------------------------------
@@ -350,7 +373,6 @@ __device__ void small_param_step(const d3r_align_desc& D, const Workspace& ws, i
 // SM independent of the warps' compute progress.
 constexpr int kStages = 3;
 constexpr int kEntTile = 16;               // entries whose per-warp partial sums are staged in smem at a time
-constexpr int kThreadsIter = kThreads;      // 8 warps (warp allocation granularity is 4: a 9th warp would cost a whole CTA/SM)
 constexpr int kRedVals = 16;               // 13 padded to 16 for the halving butterfly
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -417,26 +439,29 @@ __device__ __forceinline__ float butterfly16(float (&v)[kRedVals], int lane) {
   return v[0];
 }
 
-template <bool kL2>
-__global__ void __launch_bounds__(kThreadsIter, 2)
+template <bool kL2, int PPT>
+__global__ void __launch_bounds__(kThreads, 2)
 align_iter_kernel(const __grid_constant__ d3r_align_desc D, int it) {
+  constexpr int kSlots = PPT * kThreads;     // pixel slots of this instantiation (>= chunk_px)
   extern __shared__ __align__(128) uint8_t s_dyn[];
-  float4* s_obs = reinterpret_cast<float4*>(s_dyn);                                  // [kStages][kChunk]
-  float* s_ent = reinterpret_cast<float*>(s_dyn + kStages * kChunk * sizeof(float4)); // [kEntTile][kWarps][13]
+  float4* s_obs = reinterpret_cast<float4*>(s_dyn);                                   // [kStages][kSlots]
+  float* s_ent = reinterpret_cast<float*>(s_dyn + kStages * kSlots * sizeof(float4));  // [kEntTile][kWarps][13]
   __shared__ float s_img[kWarps * kImgVals];
   __shared__ float s_red[40];
   __shared__ int s_flag;
   __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
 
-  const Workspace ws = carve(D.workspace, D.n_imgs, D.n_edges, D.n_chunks, D.max_chunks);
+  const Workspace ws = carve(D.workspace, D.n_imgs, D.n_edges);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int chunk = blockIdx.x;
+  unsigned long long* dbg = g_align_dbg ? g_align_dbg + 4 * size_t(chunk) : nullptr;
+  if (dbg && tid == 0) dbg[0] = gtime();
   const int img = D.chunk_img[chunk];
   const int lc = chunk - D.img_chunk_ptr[img];
   const int H = D.img_hw[img * 2 + 0], W = D.img_hw[img * 2 + 1];
   const int P = H * W;
   const int pbase = lc * D.chunk_px;                       // first pixel of this CTA
-  const int npx = min(D.chunk_px, P - pbase);              // >= 1
+  const int npx = min(D.chunk_px, P - pbase);              // 1 .. kSlots
   const int64_t poff = D.img_pix_off[img];
   const int e0 = D.img_ent_ptr[img], e1 = D.img_ent_ptr[img + 1];
   const int deg = e1 - e0;
@@ -449,6 +474,9 @@ align_iter_kernel(const __grid_constant__ d3r_align_desc D, int it) {
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // slots past the chunk are never written by the bulk copies: zero them once (weight 0 -> no contribution)
+  for (int s = 0; s < kStages; ++s)
+    for (int q = npx + tid; q < kSlots; q += kThreads) s_obs[s * kSlots + q] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
 
   const uint32_t stage_bytes = uint32_t(npx) * 16u;
@@ -456,195 +484,169 @@ align_iter_kernel(const __grid_constant__ d3r_align_desc D, int it) {
     const int s = k % kStages;
     mbar_wait(smem_u32(&s_empty[s]), ((k / kStages) & 1) ^ 1);
     mbar_expect_tx(smem_u32(&s_full[s]), stage_bytes);
-    bulk_g2s(smem_u32(s_obs + s * kChunk), obs_base + D.ent_obs_off[e0 + k] + pbase, stage_bytes, smem_u32(&s_full[s]));
+    bulk_g2s(smem_u32(s_obs + s * kSlots), obs_base + D.ent_obs_off[e0 + k] + pbase, stage_bytes, smem_u32(&s_full[s]));
   };
   if (tid == 0)
     for (int k = 0; k < min(kStages, deg); ++k) produce(k);
-  {
-    // ================= compute warps =================
-    const float* iT = ws.imgT + img * kImgT;
-    float R[9], T[3];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) R[k] = iT[k];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) T[k] = iT[9 + k];
-    const float ifx = iT[12], ify = iT[13], cx = iT[14], cy = iT[15];
 
-    float X[kPPT][3], G[kPPT][3];
+  const float* iT = ws.imgT + img * kImgT;
+  float R[9], T[3];
 #pragma unroll
-    for (int k = 0; k < kPPT; ++k) {
-      const int q = tid + k * kThreads;
-      const int p = pbase + q;
-      const float ld = (q < npx) ? D.logd[poff + p] : 0.f;
-      const float d = expf(ld);
-      const int v = p / W, u = p - v * W;
-      const float c0 = d * (float(u) - cx) * ifx, c1 = d * (float(v) - cy) * ify;
-      X[k][0] = R[0] * c0 + R[1] * c1 + R[2] * d + T[0];
-      X[k][1] = R[3] * c0 + R[4] * c1 + R[5] * d + T[1];
-      X[k][2] = R[6] * c0 + R[7] * c1 + R[8] * d + T[2];
-      G[k][0] = G[k][1] = G[k][2] = 0.f;
+  for (int k = 0; k < 9; ++k) R[k] = iT[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) T[k] = iT[9 + k];
+  const float ifx = iT[12], ify = iT[13], cx = iT[14], cy = iT[15];
+
+  float X[PPT][3], G[PPT][3];
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const int q = tid + k * kThreads;
+    const int p = pbase + q;
+    const float ld = (q < npx) ? D.logd[poff + p] : 0.f;
+    const float d = expf(ld);
+    const int v = p / W, u = p - v * W;
+    const float c0 = d * (float(u) - cx) * ifx, c1 = d * (float(v) - cy) * ify;
+    X[k][0] = R[0] * c0 + R[1] * c1 + R[2] * d + T[0];
+    X[k][1] = R[3] * c0 + R[4] * c1 + R[5] * d + T[1];
+    X[k][2] = R[6] * c0 + R[7] * c1 + R[8] * d + T[2];
+    G[k][0] = G[k][1] = G[k][2] = 0.f;
+  }
+
+  __shared__ __align__(16) float s_T[kEntTile][16];   // per-entry transform M (9), t (3), coef: staged per tile
+  int stage = 0;
+  uint32_t stage_phase = 0;
+  for (int k0 = 0; k0 < deg; k0 += kEntTile) {
+    const int kend = min(deg, k0 + kEntTile);
+    // stage this tile's edge transforms in shared memory (one coalesced pass instead of 13 dependent LDGs per
+    // entry per thread sitting on the critical path of every entry)
+    if (tid < (kend - k0) * 13) {
+      const int k = tid / 13, v = tid - k * 13;
+      const int ent = e0 + k0 + k;
+      s_T[k][v] = (v < 12) ? ws.edgeT[D.ent_edge[ent] * kEdgeT + v] : D.ent_coef[ent];
     }
-
-    for (int k0 = 0; k0 < deg; k0 += kEntTile) {
-      const int kend = min(deg, k0 + kEntTile);
-      for (int kk = k0; kk < kend; ++kk) {
-        const int ent = e0 + kk;
-        const float* eT = ws.edgeT + D.ent_edge[ent] * kEdgeT;
-        float M[9], t[3];
+    __syncthreads();
+    for (int kk = k0; kk < kend; ++kk) {
+      const float4 t0 = *reinterpret_cast<const float4*>(&s_T[kk - k0][0]);
+      const float4 t1 = *reinterpret_cast<const float4*>(&s_T[kk - k0][4]);
+      const float4 t2 = *reinterpret_cast<const float4*>(&s_T[kk - k0][8]);
+      const float coef = s_T[kk - k0][12];
+      const float M[9] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w, t2.x};
+      const float t[3] = {t2.y, t2.z, t2.w};
+      const int s = stage;
+      mbar_wait(smem_u32(&s_full[s]), stage_phase);
+      if (++stage == kStages) { stage = 0; stage_phase ^= 1; }
+      const float4* so = s_obs + s * kSlots;
+      float acc[kRedVals];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) M[k] = eT[k];
+      for (int k = 0; k < kRedVals; ++k) acc[k] = 0.f;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) t[k] = eT[9 + k];
-        const float coef = D.ent_coef[ent];
-        const int s = kk % kStages;
-        mbar_wait(smem_u32(&s_full[s]), (kk / kStages) & 1);
-        const float4* so = s_obs + s * kChunk;
-        float acc[kRedVals];
-#pragma unroll
-        for (int k = 0; k < kRedVals; ++k) acc[k] = 0.f;
-#pragma unroll
-        for (int k = 0; k < kPPT; ++k) {
-          const int q = tid + k * kThreads;
-          float4 o = so[q];
-          if (q >= npx) o = make_float4(0.f, 0.f, 0.f, 0.f);   // stale smem beyond the chunk: force weight 0
-          const float qx = o.x, qy = o.y, qz = o.z;
-          const float lw = coef * o.w;
-          const float r0 = X[k][0] - (M[0] * qx + M[1] * qy + M[2] * qz + t[0]);
-          const float r1 = X[k][1] - (M[3] * qx + M[4] * qy + M[5] * qz + t[1]);
-          const float r2 = X[k][2] - (M[6] * qx + M[7] * qy + M[8] * qz + t[2]);
-          const float rho2 = r0 * r0 + r1 * r1 + r2 * r2;
-          float gs;
-          if (kL2) {
-            acc[12] += lw * rho2;
-            gs = 2.f * lw;
-          } else {
-            // torch's norm backward yields 0 at ||r|| == 0
-            const float inv = rho2 > 0.f ? rsqrtf(rho2) : 0.f;
-            acc[12] += lw * (rho2 * inv);
-            gs = lw * inv;
-          }
-          const float g0 = gs * r0, g1 = gs * r1, g2 = gs * r2;
-          G[k][0] += g0; G[k][1] += g1; G[k][2] += g2;
-          acc[0] += g0 * qx; acc[1] += g0 * qy; acc[2] += g0 * qz;
-          acc[3] += g1 * qx; acc[4] += g1 * qy; acc[5] += g1 * qz;
-          acc[6] += g2 * qx; acc[7] += g2 * qy; acc[8] += g2 * qz;
-          acc[9] += g0; acc[10] += g1; acc[11] += g2;
+      for (int k = 0; k < PPT; ++k) {
+        const float4 o = so[tid + k * kThreads];
+        const float qx = o.x, qy = o.y, qz = o.z;
+        const float lw = coef * o.w;
+        // r = X - (M q + t), written as FMA chains (the compiler may not re-associate fp32)
+        const float r0 = X[k][0] - fmaf(M[0], qx, fmaf(M[1], qy, fmaf(M[2], qz, t[0])));
+        const float r1 = X[k][1] - fmaf(M[3], qx, fmaf(M[4], qy, fmaf(M[5], qz, t[1])));
+        const float r2 = X[k][2] - fmaf(M[6], qx, fmaf(M[7], qy, fmaf(M[8], qz, t[2])));
+        const float rho2 = fmaf(r0, r0, fmaf(r1, r1, r2 * r2));
+        float gs;
+        if (kL2) {
+          acc[12] = fmaf(lw, rho2, acc[12]);
+          gs = 2.f * lw;
+        } else {
+          // torch's norm backward yields 0 at ||r|| == 0
+          const float inv = rho2 > 0.f ? rsqrtf(rho2) : 0.f;
+          acc[12] = fmaf(lw, rho2 * inv, acc[12]);
+          gs = lw * inv;
         }
-        // this warp is done with the stage: hand it back to the producer
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&s_empty[s]));
-        if (tid == 0 && kk + kStages < deg) produce(kk + kStages);   // refill the stage just drained
-        const float tot = butterfly16(acc, lane);
-        const int vi = (lane >> 1) & 15;
-        if (!(lane & 1) && vi < kEntVals) s_ent[((kk - k0) * kWarps + warp) * kEntVals + vi] = tot;
+        const float g0 = gs * r0, g1 = gs * r1, g2 = gs * r2;
+        G[k][0] += g0; G[k][1] += g1; G[k][2] += g2;
+        acc[0] = fmaf(g0, qx, acc[0]); acc[1] = fmaf(g0, qy, acc[1]); acc[2] = fmaf(g0, qz, acc[2]);
+        acc[3] = fmaf(g1, qx, acc[3]); acc[4] = fmaf(g1, qy, acc[4]); acc[5] = fmaf(g1, qz, acc[5]);
+        acc[6] = fmaf(g2, qx, acc[6]); acc[7] = fmaf(g2, qy, acc[7]); acc[8] = fmaf(g2, qz, acc[8]);
+        acc[9] += g0; acc[10] += g1; acc[11] += g2;
       }
-      // cross-warp sums of this tile of entries -> partial rows in global memory (fixed order)
-      asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
-      for (int idx = tid; idx < (kend - k0) * kEntVals; idx += kThreads) {
-        const int k = idx / kEntVals, v = idx - k * kEntVals;
-        float sacc = 0.f;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) sacc += s_ent[(k * kWarps + w) * kEntVals + v];
-        __stcg(ws.ent_part + (int64_t(e0 + k0 + k) * D.max_chunks + lc) * kEntVals + v, sacc);
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
-    }
-
-    // depth gradient + Adam (in place), per-image pose/focal sums
-    float S[kRedVals];
-#pragma unroll
-    for (int k = 0; k < kRedVals; ++k) S[k] = 0.f;
-    if (!D.eval_only) {
-      const float step_size = D.sched[it * 4 + 1], bc2s = D.sched[it * 4 + 2];
-#pragma unroll
-      for (int k = 0; k < kPPT; ++k) {
-        const int q = tid + k * kThreads;
-        if (q < npx) {
-          const int p = pbase + q;
-          const float ld = D.logd[poff + p];
-          const float d = expf(ld);
-          const int v = p / W, u = p - v * W;
-          const float c0 = d * (float(u) - cx) * ifx, c1 = d * (float(v) - cy) * ify;
-          // dX/dlogd = R c  (c is linear in d)
-          const float gd = G[k][0] * (X[k][0] - T[0]) + G[k][1] * (X[k][1] - T[1]) + G[k][2] * (X[k][2] - T[2]);
-          float m = D.logd_m[poff + p], vv = D.logd_v[poff + p];
-          const float nld = adam_update(ld, gd, m, vv, D.beta1, D.beta2, step_size, bc2s, D.adam_eps);
-          D.logd[poff + p] = nld;
-          D.logd_m[poff + p] = m;
-          D.logd_v[poff + p] = vv;
-          S[0] += G[k][0] * c0; S[1] += G[k][0] * c1; S[2] += G[k][0] * d;
-          S[3] += G[k][1] * c0; S[4] += G[k][1] * c1; S[5] += G[k][1] * d;
-          S[6] += G[k][2] * c0; S[7] += G[k][2] * c1; S[8] += G[k][2] * d;
-          S[9] += G[k][0]; S[10] += G[k][1]; S[11] += G[k][2];
-        }
-      }
-    }
-    {
-      const float tot = butterfly16(S, lane);
+      // this warp is done with the stage: hand it back, and (thread 0) refill it with entry kk + kStages
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s_empty[s]));
+      if (tid == 0 && kk + kStages < deg) produce(kk + kStages);
+      const float tot = butterfly16(acc, lane);
       const int vi = (lane >> 1) & 15;
-      if (!(lane & 1) && vi < kImgVals) s_img[warp * kImgVals + vi] = tot;
+      if (!(lane & 1) && vi < kEntVals) s_ent[((kk - k0) * kWarps + warp) * kEntVals + vi] = tot;
     }
+    // cross-warp sums of this tile of entries (fixed order) -> deterministic fixed-point accumulation
+    __syncthreads();
+    for (int idx = tid; idx < (kend - k0) * kEntVals; idx += kThreads) {
+      const int k = idx / kEntVals, v = idx - k * kEntVals;
+      float sacc = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) sacc += s_ent[(k * kWarps + w) * kEntVals + v];
+      fix_add(ws.ent_acc + int64_t(e0 + k0 + k) * kEntVals + v, sacc, ws.flags);
+    }
+    __syncthreads();
+  }
+
+  // depth gradient + Adam (in place), per-image pose/focal sums
+  float S[kRedVals];
+#pragma unroll
+  for (int k = 0; k < kRedVals; ++k) S[k] = 0.f;
+  if (!D.eval_only) {
+    const float step_size = D.sched[it * 4 + 1], bc2s = D.sched[it * 4 + 2];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      const int q = tid + k * kThreads;
+      if (q < npx) {
+        const int p = pbase + q;
+        const float ld = D.logd[poff + p];
+        const float d = expf(ld);
+        const int v = p / W, u = p - v * W;
+        const float c0 = d * (float(u) - cx) * ifx, c1 = d * (float(v) - cy) * ify;
+        // dX/dlogd = R c  (c is linear in d)
+        const float gd = G[k][0] * (X[k][0] - T[0]) + G[k][1] * (X[k][1] - T[1]) + G[k][2] * (X[k][2] - T[2]);
+        float m = D.logd_m[poff + p], vv = D.logd_v[poff + p];
+        const float nld = adam_update(ld, gd, m, vv, D.beta1, D.beta2, step_size, bc2s, D.adam_eps);
+        D.logd[poff + p] = nld;
+        D.logd_m[poff + p] = m;
+        D.logd_v[poff + p] = vv;
+        S[0] += G[k][0] * c0; S[1] += G[k][0] * c1; S[2] += G[k][0] * d;
+        S[3] += G[k][1] * c0; S[4] += G[k][1] * c1; S[5] += G[k][1] * d;
+        S[6] += G[k][2] * c0; S[7] += G[k][2] * c1; S[8] += G[k][2] * d;
+        S[9] += G[k][0]; S[10] += G[k][1]; S[11] += G[k][2];
+      }
+    }
+  }
+  {
+    const float tot = butterfly16(S, lane);
+    const int vi = (lane >> 1) & 15;
+    if (!(lane & 1) && vi < kImgVals) s_img[warp * kImgVals + vi] = tot;
   }
   __syncthreads();
   if (tid < kImgVals) {
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) s += s_img[w * kImgVals + tid];
-    __stcg(ws.img_part + int64_t(chunk) * kImgVals + tid, s);
+    fix_add(ws.img_acc + int64_t(img) * kImgVals + tid, s, ws.flags);
   }
+  if (dbg && tid == 0) dbg[1] = gtime();
 
-  // ---- ticket 1: last CTA of this image reduces the image's partial rows ----
+  // ---- grid ticket: the last CTA to finish runs the small-parameter step ----
   __threadfence();
   __syncthreads();
-  const int nchunk_img = D.img_chunk_ptr[img + 1] - D.img_chunk_ptr[img];
-  if (tid == 0) s_flag = (atomicAdd(D.counters + img, 1) == nchunk_img - 1);
+  if (tid == 0) s_flag = (atomicAdd(D.counters, 1) == int(gridDim.x) - 1);
   __syncthreads();
-  if (!s_flag) return;
-  __threadfence();
-  // one warp per (entry, value) row: lanes take chunks round-robin (independent loads in flight), then a fixed
-  // shuffle tree -> deterministic and ~100x shorter than a serial walk over the chunks
-  for (int task = warp; task < deg * kEntVals + kImgVals; task += kWarps) {
-    const float* src;
-    float* dst;
-    int stride;
-    if (task < deg * kEntVals) {
-      const int k = task / kEntVals, v = task - k * kEntVals;
-      src = ws.ent_part + int64_t(e0 + k) * D.max_chunks * kEntVals + v;
-      dst = ws.ent_sum + (e0 + k) * kEntVals + v;
-      stride = kEntVals;
-    } else {
-      const int v = task - deg * kEntVals;
-      src = ws.img_part + int64_t(D.img_chunk_ptr[img]) * kImgVals + v;
-      dst = ws.img_sum + img * kImgVals + v;
-      stride = kImgVals;
-    }
-    float sacc = 0.f;
-    for (int c0 = 0; c0 < nchunk_img; c0 += 128) {   // 4 independent loads per lane in flight
-      const int ca = c0 + lane, cb = ca + 32, cc = ca + 64, cd = ca + 96;
-      const float va = ca < nchunk_img ? __ldcg(src + ca * stride) : 0.f;
-      const float vb = cb < nchunk_img ? __ldcg(src + cb * stride) : 0.f;
-      const float vc = cc < nchunk_img ? __ldcg(src + cc * stride) : 0.f;
-      const float vd = cd < nchunk_img ? __ldcg(src + cd * stride) : 0.f;
-      sacc += (va + vb) + (vc + vd);
-    }
-    sacc = warp_sum(sacc);
-    if (lane == 0) __stcg(dst, sacc);
+  if (!s_flag) {
+    if (dbg && tid == 0) dbg[2] = gtime();
+    return;
   }
-  if (tid == 0) D.counters[img] = 0;  // re-arm for the next launch
-
-  // ---- ticket 2: last image finisher updates the small parameters ----
   __threadfence();
-  __syncthreads();
-  if (tid == 0) s_flag = (atomicAdd(D.counters + D.n_imgs, 1) == D.n_imgs - 1);
-  __syncthreads();
-  if (!s_flag) return;
-  __threadfence();
-  if (tid == 0) D.counters[D.n_imgs] = 0;
+  if (tid == 0) D.counters[0] = 0;   // re-arm for the next launch
+  if (dbg && tid == 0) dbg[2] = gtime();
   small_param_step(D, ws, it, s_red);
+  if (dbg && tid == 0) dbg[3] = gtime();
 }
 
 __global__ void __launch_bounds__(kThreads) pts3d_kernel(const __grid_constant__ d3r_align_desc D, float* out) {
-  const Workspace ws = carve(D.workspace, D.n_imgs, D.n_edges, D.n_chunks, D.max_chunks);
+  const Workspace ws = carve(D.workspace, D.n_imgs, D.n_edges);
   const int chunk = blockIdx.x;
   const int img = D.chunk_img[chunk];
   const int lc = chunk - D.img_chunk_ptr[img];
@@ -676,11 +678,18 @@ __global__ void pack_obs_kernel(const float* __restrict__ pts, const float* __re
 using namespace d3r;
 using namespace d3r::align;
 
+extern "C" int d3r_align_set_debug(void* dev_buf) {
+  unsigned long long* p = reinterpret_cast<unsigned long long*>(dev_buf);
+  D3R_CUDA(cudaMemcpyToSymbol(g_align_dbg, &p, sizeof(p)));
+  return D3R_OK;
+}
+
 extern "C" int d3r_align_chunk_pixels(void) { return kChunk; }
 extern "C" int d3r_sizeof_align_desc(void) { return (int)sizeof(d3r_align_desc); }
 
 extern "C" int64_t d3r_align_workspace_floats(int32_t n_imgs, int32_t n_edges, int32_t n_chunks, int32_t max_chunks) {
-  return workspace_floats(n_imgs, n_edges, n_chunks, max_chunks);
+  (void)n_chunks; (void)max_chunks;   // kept in the signature for ABI stability; accumulators are per entry now
+  return workspace_floats(n_imgs, n_edges);
 }
 
 static int validate(const d3r_align_desc* d) {
@@ -702,26 +711,47 @@ extern "C" int d3r_align_prepare(const d3r_align_desc* desc, void* stream) {
   return D3R_OK;
 }
 
+template <bool kL2, int PPT>
+static int launch_iters(const d3r_align_desc* desc, int it_begin, int it_end, cudaStream_t st) {
+  const size_t smem = size_t(kStages) * PPT * kThreads * sizeof(float4) + size_t(kEntTile) * kWarps * kEntVals * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    D3R_CUDA(cudaFuncSetAttribute(align_iter_kernel<kL2, PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // two CTAs per SM need the maximum shared-memory carve-out
+    D3R_CUDA(cudaFuncSetAttribute(align_iter_kernel<kL2, PPT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr = true;
+  }
+  for (int it = it_begin; it < it_end; ++it) align_iter_kernel<kL2, PPT><<<desc->n_chunks, kThreads, smem, st>>>(*desc, it);
+  D3R_LAUNCH_CHECK();
+  return D3R_OK;
+}
+
+template <bool kL2>
+static int launch_ppt(const d3r_align_desc* desc, int it_begin, int it_end, cudaStream_t st) {
+  const int ppt = (desc->chunk_px + kThreads - 1) / kThreads;   // pixel slots per thread this problem needs
+  if (ppt <= 4) return launch_iters<kL2, 4>(desc, it_begin, it_end, st);
+  if (ppt == 5) return launch_iters<kL2, 5>(desc, it_begin, it_end, st);
+  if (ppt == 6) return launch_iters<kL2, 6>(desc, it_begin, it_end, st);
+  if (ppt == 7) return launch_iters<kL2, 7>(desc, it_begin, it_end, st);
+  return launch_iters<kL2, 8>(desc, it_begin, it_end, st);
+}
+
 extern "C" int d3r_align_run(const d3r_align_desc* desc, int32_t it_begin, int32_t it_end, void* stream) {
   int rc = validate(desc);
   if (rc) return rc;
   D3R_CHECK_ARG(it_begin >= 0 && it_end >= it_begin, "d3r_align_run: bad iteration range");
-  const size_t smem = size_t(kStages) * kChunk * sizeof(float4) + size_t(kEntTile) * kWarps * kEntVals * sizeof(float);
-  if (desc->dist_l2) {
-    D3R_CUDA(cudaFuncSetAttribute(align_iter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    D3R_CUDA(cudaFuncSetAttribute(align_iter_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  } else {
-    D3R_CUDA(cudaFuncSetAttribute(align_iter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    D3R_CUDA(cudaFuncSetAttribute(align_iter_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  }
   prof::Scope scope("align_iter", (cudaStream_t)stream, 0.0, 0.0, it_end - it_begin);
-  for (int it = it_begin; it < it_end; ++it) {
-    if (desc->dist_l2)
-      align_iter_kernel<true><<<desc->n_chunks, kThreadsIter, smem, (cudaStream_t)stream>>>(*desc, it);
-    else
-      align_iter_kernel<false><<<desc->n_chunks, kThreadsIter, smem, (cudaStream_t)stream>>>(*desc, it);
-  }
-  D3R_LAUNCH_CHECK();
+  return desc->dist_l2 ? launch_ppt<true>(desc, it_begin, it_end, (cudaStream_t)stream)
+                       : launch_ppt<false>(desc, it_begin, it_end, (cudaStream_t)stream);
+}
+
+/* 1 if a fixed-point accumulator overflowed (|partial sum| >= 2^18) since the flag was last cleared. */
+extern "C" int d3r_align_overflow_flag(const d3r_align_desc* desc, int32_t* host_out, void* stream) {
+  int rc = validate(desc);
+  if (rc) return rc;
+  const Workspace ws = carve(desc->workspace, desc->n_imgs, desc->n_edges);
+  D3R_CUDA(cudaMemcpyAsync(host_out, ws.flags, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  D3R_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return D3R_OK;
 }
 

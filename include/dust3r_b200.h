@@ -113,6 +113,7 @@ typedef struct d3r_align_desc {
   const float* sched;
   float* loss_out;              /* [niter_total] loss of every iteration                    */
   int32_t* counters;            /* [n + 2] zero-initialised by the caller once              */
+  /* `workspace` must be zero-initialised by the caller once as well (accumulators live there).  */
 } d3r_align_desc;
 
 /* sizeof(d3r_align_desc) as compiled into the library (binding self-check). */
@@ -126,9 +127,15 @@ int64_t d3r_align_workspace_floats(int32_t n_imgs, int32_t n_edges, int32_t n_ch
 int d3r_align_prepare(const d3r_align_desc* desc, void* stream);
 /* Runs iterations [it_begin, it_end) (indices into sched / loss_out).  Asynchronous. */
 int d3r_align_run(const d3r_align_desc* desc, int32_t it_begin, int32_t it_end, void* stream);
+/* Cross-CTA sums use order-independent 2^44 fixed-point integer atomics (bit-reproducible).  *host_out = 1 when a
+ * partial sum left their range (|x| >= 2^18: unreasonably scaled scene) since the workspace was zeroed. */
+int d3r_align_overflow_flag(const d3r_align_desc* desc, int32_t* host_out, void* stream);
 /* World-frame pointmaps X[i] = R_i * unproject(depth_i) + T_i for every image
  * (PointCloudOptimizer.depth_to_pts3d, optimizer.py:170-180).  out: [sum P_i][3] float. */
 int d3r_align_pts3d(const d3r_align_desc* desc, float* out_dev, void* stream);
+/* Debug aid: when dev_buf != NULL every CTA of the next alignment launches writes 4 uint64 %globaltimer stamps
+ * (start, end of pixel phase, end/exit, end of small-parameter step) at dev_buf[4*cta]. */
+int d3r_align_set_debug(void* dev_buf);
 /* Packs pred (P,3) + weight (P) rows into the float4 observation layout. */
 int d3r_align_pack_obs(const float* pts_dev, const float* weight_dev, void* obs_dev, int64_t obs_off,
                        int64_t n_pix, void* stream);
