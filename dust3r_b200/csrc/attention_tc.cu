@@ -182,11 +182,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
     const uint32_t t_s = tmem_base + lane_addr + kColS, t_o = tmem_base + lane_addr + kColO;
-    // m_ref: the exponent reference currently baked into O and l.  It only follows the true running max when
-    // that max has moved by more than 2^kLazy (lazy rescaling): p may then exceed 1 by at most 2^kLazy, which
-    // fp32 sums / bf16 P absorb, and the tcgen05.ld/st round trip over O is skipped for most blocks.
+    // m_ref: the exponent reference baked into P, O and l.  Any fixed reference gives the same softmax after the
+    // final division, so blocks j >= 1 exponentiate against the reference they inherit (no separate max pass on
+    // their critical path) while tracking the block max alongside the MUFU-bound exp loop.  Only when a row max
+    // outgrows the reference by more than 2^kLazy is the reference moved: O (TMEM) and l are multiplied by the
+    // correction before the next P V accumulates (p <= 2^kLazy in between, harmless in fp32 / bf16).
     constexpr float kLazy = 8.f;
-    float m_ref = -INFINITY, l = 0.f;
+    float m_ref = -INFINITY, l = 0.f, corr_pending = 1.f;
+    bool pending = false;
     for (int j = 0; j < nblk; ++j) {
       const int nvalid = min(BK, Nk - j * BK);
       ptx::mbar_wait(ptx::smem_u32(s_ready), j & 1);
@@ -199,27 +202,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(s_free));
-      float mx = -INFINITY;
-      if (nvalid == BK) {
+      if (nvalid < BK) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(sr[i]));
-      } else {
-#pragma unroll
-        for (int i = 0; i < 128; ++i) {
-          if (i >= nvalid) sr[i] = 0xff800000u;  // -inf
-          mx = fmaxf(mx, __uint_as_float(sr[i]));
-        }
+        for (int i = 0; i < 128; ++i)
+          if (i >= nvalid) sr[i] = 0xff800000u;  // -inf -> p = 0
       }
-      // rescale decision (warp-uniform so the tcgen05.ld/st below stay convergent)
-      const bool grow = (mx - m_ref) * scale_log2 > kLazy;
-      const bool rescale = (j > 0) && __any_sync(0xffffffffu, grow);
-      float corr = 1.f;
       if (j == 0) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 128; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(sr[i]), __uint_as_float(sr[i + 1])));
         m_ref = mx;
-      } else if (rescale) {
-        const float m_new = fmaxf(m_ref, mx);
-        corr = fast_exp2((m_ref - m_new) * scale_log2);
-        m_ref = m_new;
       }
       const float ms = m_ref * scale_log2;
       // the previous P V must have consumed P (smem) and updated O before we touch either
@@ -227,29 +219,34 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         ptx::mbar_wait(ptx::smem_u32(o_done), (j - 1) & 1);
         ptx::tc_fence_after();
       }
-      if (rescale) {
+      if (pending) {   // warp-uniform
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(t_o + c * 32, r);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr_pending);
           tmem_st_32x32b_x32(t_o + c * 32, r);
         }
         tmem_st_wait();
+        pending = false;
       }
-      // p = exp2(s*c - m_ref*c), row sum, bf16 pack, swizzled store (K-major SW128: 16-B chunk ^ (row & 7))
-      float rs0 = 0.f, rs1 = 0.f;
+      // p = exp2(s*c - m_ref*c), row sum, running block max, bf16 pack, swizzled store (K-major SW128:
+      // 16-byte chunk index ^ (row & 7))
+      float rs0 = 0.f, rs1 = 0.f, bm0 = -INFINITY, bm1 = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t packed[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[c * 32 + i]), scale_log2, -ms));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[c * 32 + i + 1]), scale_log2, -ms));
+          const float s0 = __uint_as_float(sr[c * 32 + i]), s1 = __uint_as_float(sr[c * 32 + i + 1]);
+          const float p0 = fast_exp2(fmaf(s0, scale_log2, -ms));
+          const float p1 = fast_exp2(fmaf(s1, scale_log2, -ms));
           rs0 += p0;
           rs1 += p1;
+          bm0 = fmaxf(bm0, s0);
+          bm1 = fmaxf(bm1, s1);
           packed[i >> 1] = pack2(p0, p1);
         }
         uint8_t* atom = s_p + (c >> 1) * kTileBytes + row * 128;
@@ -260,17 +257,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
               make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
         }
       }
-      l = l * corr + (rs0 + rs1);
+      l += rs0 + rs1;
       // make the generic-proxy smem writes of P visible to the tensor core (async proxy), then publish
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(p_ready));
+      // move the reference if some row of this warp outgrew it (decision is warp-uniform so the TMEM round trip
+      // above stays convergent); applied before the next block's P V
+      const float bmax = fmaxf(bm0, bm1);
+      if (__any_sync(0xffffffffu, (bmax - m_ref) * scale_log2 > kLazy)) {
+        const float m_new = fmaxf(m_ref, bmax);
+        corr_pending = fast_exp2((m_ref - m_new) * scale_log2);
+        l *= corr_pending;
+        m_ref = m_new;
+        pending = true;
+      }
     }
     // ---- epilogue: O / l -> bf16 -> global ----
     ptx::mbar_wait(ptx::smem_u32(o_done), (nblk - 1) & 1);
     ptx::tc_fence_after();
-    const float inv = 1.f / l;
+    const float inv = (pending ? corr_pending : 1.f) / l;   // a correction decided after the last block still applies to O
     const int qrow = q0 + row;
     __nv_bfloat16* orow = out + ((long long)b * Nq + qrow) * ldo + h * D;
 #pragma unroll 1

@@ -98,6 +98,21 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.f + copysignf(e, x));
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): a lane moves one whole 32-byte sector per instruction,
+// so the row-per-thread epilogue writes full sectors instead of two 16-byte halves
+__device__ __forceinline__ void st256(void* p, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]),
+               "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void ld256(const void* p, uint32_t* r) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]),
+               "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+}
+__device__ __forceinline__ void ld256_nc(const void* p, uint32_t* r) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]),
+               "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -323,30 +338,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           off = row_off + col0;
         }
         if (flags & F_ADD0) {
-          const uint4* a = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.add0) + off);
+          const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(p.add0) + off;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 q = __ldg(a + j);
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+          for (int j = 0; j < 2; ++j) {
+            uint32_t w[8];
+            ld256_nc(a + 16 * j, w);
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
+            for (int t = 0; t < 8; ++t) {
               const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[t]);
-              v[8 * j + 2 * t] += __low2float(h);
-              v[8 * j + 2 * t + 1] += __high2float(h);
+              v[16 * j + 2 * t] += __low2float(h);
+              v[16 * j + 2 * t + 1] += __high2float(h);
             }
           }
         }
         if (flags & F_ADD1) {
-          const uint4* a = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.add1) + off);
+          const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(p.add1) + off;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 q = __ldg(a + j);
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+          for (int j = 0; j < 2; ++j) {
+            uint32_t w[8];
+            ld256_nc(a + 16 * j, w);
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
+            for (int t = 0; t < 8; ++t) {
               const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[t]);
-              v[8 * j + 2 * t] += __low2float(h);
-              v[8 * j + 2 * t + 1] += __high2float(h);
+              v[16 * j + 2 * t] += __low2float(h);
+              v[16 * j + 2 * t + 1] += __high2float(h);
             }
           }
         }
@@ -355,37 +370,51 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         if (flags & (F_OUT_F32 | F_RESID_INPLACE)) {
-          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off);
+          float* o = reinterpret_cast<float*>(p.out) + off;
           if (flags & F_RESID_INPLACE) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 r = o[j];
-              v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+            for (int j = 0; j < 4; ++j) {
+              uint32_t w[8];
+              ld256(o + 8 * j, w);
+#pragma unroll
+              for (int t = 0; t < 8; ++t) v[8 * j + t] += __uint_as_float(w[t]);
             }
           }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          if (flags & F_OUT2_BF16) {
-            uint4* o2 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + off);
+          for (int j = 0; j < 4; ++j) {
+            uint32_t w[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              o2[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                 pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+            for (int t = 0; t < 8; ++t) w[t] = __float_as_uint(v[8 * j + t]);
+            st256(o + 8 * j, w);
+          }
+          if (flags & F_OUT2_BF16) {
+            __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + off;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              uint32_t w[8];
+#pragma unroll
+              for (int t = 0; t < 8; ++t) w[t] = pack_bf16(v[16 * j + 2 * t], v[16 * j + 2 * t + 1]);
+              st256(o2 + 16 * j, w);
+            }
           }
         } else {
-          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            o[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                              pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+          for (int j = 0; j < 2; ++j) {
+            uint32_t w[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) w[t] = pack_bf16(v[16 * j + 2 * t], v[16 * j + 2 * t + 1]);
+            st256(o + 16 * j, w);
+          }
           if (flags & F_OUT2_RELU) {
-            uint4* o2 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + off);
+            __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + off;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              o2[j] = make_uint4(pack_bf16(fmaxf(v[8 * j], 0.f), fmaxf(v[8 * j + 1], 0.f)),
-                                 pack_bf16(fmaxf(v[8 * j + 2], 0.f), fmaxf(v[8 * j + 3], 0.f)),
-                                 pack_bf16(fmaxf(v[8 * j + 4], 0.f), fmaxf(v[8 * j + 5], 0.f)),
-                                 pack_bf16(fmaxf(v[8 * j + 6], 0.f), fmaxf(v[8 * j + 7], 0.f)));
+            for (int j = 0; j < 2; ++j) {
+              uint32_t w[8];
+#pragma unroll
+              for (int t = 0; t < 8; ++t) w[t] = pack_bf16(fmaxf(v[16 * j + 2 * t], 0.f), fmaxf(v[16 * j + 2 * t + 1], 0.f));
+              st256(o2 + 16 * j, w);
+            }
           }
         }
       }
