@@ -214,6 +214,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         m_ref = mx;
       }
       const float ms = m_ref * scale_log2;
+      // p = exp2(s*c - m_ref*c), row sum, running block max, bf16 pack -- all in registers: the MUFU-bound part
+      // of the block does not depend on the previous P V, so it runs while that MMA is still in flight
+      float rs0 = 0.f, rs1 = 0.f, bm0 = -INFINITY, bm1 = -INFINITY;
+      uint32_t packed[64];
+#pragma unroll
+      for (int i = 0; i < 128; i += 2) {
+        const float s0 = __uint_as_float(sr[i]), s1 = __uint_as_float(sr[i + 1]);
+        const float p0 = fast_exp2(fmaf(s0, scale_log2, -ms));
+        const float p1 = fast_exp2(fmaf(s1, scale_log2, -ms));
+        rs0 += p0;
+        rs1 += p1;
+        bm0 = fmaxf(bm0, s0);
+        bm1 = fmaxf(bm1, s1);
+        packed[i >> 1] = pack2(p0, p1);
+      }
       // the previous P V must have consumed P (smem) and updated O before we touch either
       if (j > 0) {
         ptx::mbar_wait(ptx::smem_u32(o_done), (j - 1) & 1);
@@ -232,29 +247,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         tmem_st_wait();
         pending = false;
       }
-      // p = exp2(s*c - m_ref*c), row sum, running block max, bf16 pack, swizzled store (K-major SW128:
-      // 16-byte chunk index ^ (row & 7))
-      float rs0 = 0.f, rs1 = 0.f, bm0 = -INFINITY, bm1 = -INFINITY;
+      // swizzled store of P (K-major SW128: 16-byte chunk index ^ (row & 7))
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t packed[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float s0 = __uint_as_float(sr[c * 32 + i]), s1 = __uint_as_float(sr[c * 32 + i + 1]);
-          const float p0 = fast_exp2(fmaf(s0, scale_log2, -ms));
-          const float p1 = fast_exp2(fmaf(s1, scale_log2, -ms));
-          rs0 += p0;
-          rs1 += p1;
-          bm0 = fmaxf(bm0, s0);
-          bm1 = fmaxf(bm1, s1);
-          packed[i >> 1] = pack2(p0, p1);
-        }
         uint8_t* atom = s_p + (c >> 1) * kTileBytes + row * 128;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int chunk = (c & 1) * 4 + q;
           *reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) =
-              make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+              make_uint4(packed[c * 16 + 4 * q], packed[c * 16 + 4 * q + 1], packed[c * 16 + 4 * q + 2], packed[c * 16 + 4 * q + 3]);
         }
       }
       l += rs0 + rs1;

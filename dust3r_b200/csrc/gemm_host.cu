@@ -71,12 +71,12 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
 }
 
 // 0: 1-CTA kernels, 1: CTA-pair (cta_group::2) kernels whenever BLOCK_N >= 128, 2 (default): pair kernels when
-// the mainloop dominates the tile (>= 32 k-blocks: fc2, the 3x3 convolutions), 1-CTA kernels otherwise (short-K
-// tiles are epilogue-bound and gain nothing from halving the operand traffic; measured in
-// profiles/r01_gemm_impl_compare.jsonl)
+// the mainloop is long enough to dominate the tile (>= 16 k-blocks, i.e. K >= 1024: every encoder GEMM, fc2 of
+// the decoder, the 3x3 convolutions), 1-CTA kernels for the short-K decoder projections which stay
+// epilogue-bound (measured: profiles/r01_gemm_impl_compare*.jsonl)
 static int g_impl = 2;
 void set_impl(int impl) { g_impl = impl; }
-bool use_pair(int bn, int num_kb) { return bn >= 128 && (g_impl == 1 || (g_impl == 2 && num_kb >= 32)); }
+bool use_pair(int bn, int num_kb) { return bn >= 128 && (g_impl == 1 || (g_impl == 2 && num_kb >= 16)); }
 
 template <int BN>
 static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int m_tiles, int n_tiles, cudaStream_t st) {

@@ -180,7 +180,7 @@ int d3r_attention_hd64(const void* q_dev, int64_t ldq, const void* k_dev, int64_
                        void* stream);
 
 /* Selects the GEMM / conv kernel family: 0 = 1-CTA tcgen05 kernels, 1 = CTA-pair (cta_group::2) kernels,
- * 2 (default) = CTA-pair kernels for long-K problems (>= 32 k-blocks of 64), 1-CTA otherwise. */
+ * 2 (default) = CTA-pair kernels for long-K problems (>= 16 k-blocks of 64), 1-CTA otherwise. */
 void d3r_set_gemm_impl(int32_t impl);
 
 /* Selects the attention kernel: 0 = mma.sync streaming kernel, 1 = tcgen05/TMEM kernel. */

@@ -46,7 +46,7 @@ def forward(Bp):
 
 if __name__ == '__main__':
     lib = _lib.get_lib()
-    for impl in (0, 2):
+    for impl in (2, 1):
         lib.d3r_set_gemm_impl(impl)
         print(json.dumps(dict(kind='gemm_impl', impl=impl)), flush=True)
         gemm_shapes()
