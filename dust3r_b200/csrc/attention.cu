@@ -199,6 +199,9 @@ int attention_hd64(const void* q, long long ldq, const void* k, long long ldk, c
 }  // namespace attn
 }  // namespace d3r
 
+namespace d3r { namespace attn { int attention_set_debug(void* dev_buf); } }
+extern "C" int d3r_attention_set_debug(void* dev_buf) { return d3r::attn::attention_set_debug(dev_buf); }
+
 extern "C" void d3r_set_attention_impl(int32_t impl) { d3r::attn::set_impl(impl); }
 
 extern "C" int d3r_attention_hd64(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,

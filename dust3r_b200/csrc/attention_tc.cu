@@ -24,14 +24,15 @@ namespace attn {
 
 namespace tc {
 
-constexpr int BQ = 128, BK = 128, D = 64;
+constexpr int BQ = 128, BK = 64, D = 64;   // 64-key blocks: 64 KB smem + 128 TMEM columns per CTA -> 3 CTAs / SM
 constexpr int kThreads = 192;
-constexpr int kTileBytes = 128 * 64 * 2;  // 16 KB: 128 rows x 128 B
-// 7 tiles + barriers = 112.1 KB: two CTAs (+1 KB reserved each) fit the 228 KB of an SM
-constexpr int kSmemBytes = kTileBytes /*Q*/ + 2 * kTileBytes /*K ring*/ + 2 * kTileBytes /*V ring*/ +
-                           2 * kTileBytes /*P: two 64-key atoms*/ + 128 /*barriers*/;
-constexpr int kTmemCols = 256;
-constexpr uint32_t kColS = 0, kColO = 128;
+constexpr int kTileBytes = 128 * 64 * 2;  // 16 KB: 128 rows x 128 B (Q tile, one P atom)
+constexpr int kKVBytes = BK * 64 * 2;     // one K or V block: BK rows x 128 B
+constexpr int kCTAsPerSM = (BK == 64) ? 3 : 2;
+constexpr int kSmemBytes = kTileBytes /*Q*/ + 2 * kKVBytes /*K ring*/ + 2 * kKVBytes /*V ring*/ +
+                           (BK / 64) * kTileBytes /*P: one SW128 atom per 64 keys*/ + 128 /*barriers*/;
+constexpr int kTmemCols = (BK + 64 <= 128) ? 128 : 256;
+constexpr uint32_t kColS = 0, kColO = BK;
 
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t* r) {
   asm volatile(
@@ -68,7 +69,16 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+// optional timeline instrumentation (debug aid)
+__device__ unsigned long long* g_attn_dbg = nullptr;
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define ATT_STAMP(slot) do { if (dbg && (slot) < 32) dbg[(slot)] = gtime(); } while (0)
+
+__global__ void __launch_bounds__(kThreads, kCTAsPerSM)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const __grid_constant__ CUtensorMap tmap_v, __nv_bfloat16* __restrict__ out, long long ldo, int Nq, int Nk,
                     int q_col0, int k_col0, int v_col0, float scale_log2) {
@@ -76,9 +86,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
   uint8_t* s_q = smem;
   uint8_t* s_k = s_q + kTileBytes;
-  uint8_t* s_v = s_k + 2 * kTileBytes;
-  uint8_t* s_p = s_v + 2 * kTileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 2 * kTileBytes);
+  uint8_t* s_v = s_k + 2 * kKVBytes;
+  uint8_t* s_p = s_v + 2 * kKVBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + (BK / 64) * kTileBytes);
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;    // [2]
   uint64_t* k_empty = bars + 3;   // [2]
@@ -93,6 +103,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
   const int nblk = (Nk + BK - 1) / BK;
+  // 64 stamps per traced CTA: [0..31] softmax thread (row 0 of warp 2), [32..63] MMA thread
+  unsigned long long* dbg = nullptr;
+  if (g_attn_dbg && blockIdx.x == 2 && blockIdx.y == 3) {
+    if (threadIdx.x == 64) dbg = g_attn_dbg + size_t(blockIdx.z) * 64;
+    if (threadIdx.x == 32) dbg = g_attn_dbg + size_t(blockIdx.z) * 64 + 32;
+  }
+  ATT_STAMP(0);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_q);
@@ -132,17 +149,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const int st = j & 1;
         const uint32_t ph = (j >> 1) & 1;
         ptx::mbar_wait(ptx::smem_u32(&k_empty[st]), ph ^ 1);
-        ptx::mbar_arrive_expect_tx(ptx::smem_u32(&k_full[st]), kTileBytes);
-        ptx::tma_load_3d(ptx::smem_u32(s_k + st * kTileBytes), &tmap_k, ptx::smem_u32(&k_full[st]), k_col0 + h * D, j * BK, b);
+        ptx::mbar_arrive_expect_tx(ptx::smem_u32(&k_full[st]), kKVBytes);
+        ptx::tma_load_3d(ptx::smem_u32(s_k + st * kKVBytes), &tmap_k, ptx::smem_u32(&k_full[st]), k_col0 + h * D, j * BK, b);
         ptx::mbar_wait(ptx::smem_u32(&v_empty[st]), ph ^ 1);
-        ptx::mbar_arrive_expect_tx(ptx::smem_u32(&v_full[st]), kTileBytes);
-        ptx::tma_load_3d(ptx::smem_u32(s_v + st * kTileBytes), &tmap_v, ptx::smem_u32(&v_full[st]), v_col0 + h * D, j * BK, b);
+        ptx::mbar_arrive_expect_tx(ptx::smem_u32(&v_full[st]), kKVBytes);
+        ptx::tma_load_3d(ptx::smem_u32(s_v + st * kKVBytes), &tmap_v, ptx::smem_u32(&v_full[st]), v_col0 + h * D, j * BK, b);
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (ptx::elect_one()) {
-      constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, BK, 0, 0);
       constexpr uint32_t idesc_o = ptx::umma_idesc_bf16(128, 64, 0, 1);  // B (=V) is MN-major
       const uint32_t d_s = tmem_base + kColS, d_o = tmem_base + kColO;
       const uint64_t dq = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(s_q));
@@ -151,11 +168,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         ptx::mbar_wait(ptx::smem_u32(&k_full[st]), (j >> 1) & 1);
         if (j > 0) ptx::mbar_wait(ptx::smem_u32(s_free), (j - 1) & 1);  // softmax has drained S_{j-1}
         ptx::tc_fence_after();
-        const uint64_t dk = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(s_k + st * kTileBytes));
+        const uint64_t dk = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(s_k + st * kKVBytes));
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) ptx::umma_bf16_ss(d_s, dq + uint64_t(2 * k), dk + uint64_t(2 * k), idesc_s, k ? 1u : 0u);
         ptx::umma_commit(ptx::smem_u32(&k_empty[st]));
         ptx::umma_commit(ptx::smem_u32(s_ready));
+        ATT_STAMP(1 + j * 3);
       };
       ptx::mbar_wait(ptx::smem_u32(q_full), 0);
       issue_s(0);
@@ -163,9 +181,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         if (j + 1 < nblk) issue_s(j + 1);
         const int st = j & 1;
         ptx::mbar_wait(ptx::smem_u32(p_ready), j & 1);
+        ATT_STAMP(2 + j * 3);
         ptx::mbar_wait(ptx::smem_u32(&v_full[st]), (j >> 1) & 1);
         ptx::tc_fence_after();
-        const uint32_t pv = ptx::smem_u32(s_v + st * kTileBytes);
+        const uint32_t pv = ptx::smem_u32(s_v + st * kKVBytes);
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           const uint64_t dp = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(s_p) + (k >> 2) * kTileBytes) + uint64_t(2 * (k & 3));
@@ -174,6 +193,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         }
         ptx::umma_commit(ptx::smem_u32(&v_empty[st]));
         ptx::umma_commit(ptx::smem_u32(o_done));
+        ATT_STAMP(3 + j * 3);
       }
     }
   } else {
@@ -192,48 +212,77 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     bool pending = false;
     for (int j = 0; j < nblk; ++j) {
       const int nvalid = min(BK, Nk - j * BK);
+      ATT_STAMP(1 + j * 5);
       ptx::mbar_wait(ptx::smem_u32(s_ready), j & 1);
       ptx::tc_fence_after();
-      // whole S row -> registers (single TMEM pass), then release S for the next Q K^T immediately
-      uint32_t sr[128];
+      ATT_STAMP(2 + j * 5);
+      float rs0 = 0.f, rs1 = 0.f, bm0 = -INFINITY, bm1 = -INFINITY;
+      uint32_t packed[BK / 2];
+      float ms;
+      // p = exp2(s*c - m_ref*c), row sum, running block max, bf16 pack -- all in registers: the MUFU-bound part of
+      // the block does not depend on the previous P V, so it runs while that MMA is still in flight.
+      auto exp_chunk = [&](const uint32_t* r, int c) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) ptx::tmem_ld_32x32b_x32(t_s + c * 32, sr + c * 32);
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(s_free));
-      if (nvalid < BK) {
-#pragma unroll
-        for (int i = 0; i < 128; ++i)
-          if (i >= nvalid) sr[i] = 0xff800000u;  // -inf -> p = 0
-      }
+        for (int i = 0; i < 32; i += 2) {
+          float s0 = __uint_as_float(r[i]), s1 = __uint_as_float(r[i + 1]);
+          if (nvalid < BK) {   // ragged last key block: masked keys contribute p = 0
+            if (c * 32 + i >= nvalid) s0 = -INFINITY;
+            if (c * 32 + i + 1 >= nvalid) s1 = -INFINITY;
+          }
+          const float p0 = fast_exp2(fmaf(s0, scale_log2, -ms));
+          const float p1 = fast_exp2(fmaf(s1, scale_log2, -ms));
+          rs0 += p0;
+          rs1 += p1;
+          bm0 = fmaxf(bm0, s0);
+          bm1 = fmaxf(bm1, s1);
+          packed[c * 16 + (i >> 1)] = pack2(p0, p1);
+        }
+      };
+      constexpr int kChunks = BK / 32;
       if (j == 0) {
+        // first block: the reference is this block's row max, so the whole row is needed before any exp
+        uint32_t sr[BK];
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) ptx::tmem_ld_32x32b_x32(t_s + c * 32, sr + c * 32);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(s_free));
         float mx = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 128; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(sr[i]), __uint_as_float(sr[i + 1])));
+        for (int i = 0; i < BK; ++i)
+          if (i < nvalid) mx = fmaxf(mx, __uint_as_float(sr[i]));
         m_ref = mx;
-      }
-      const float ms = m_ref * scale_log2;
-      // p = exp2(s*c - m_ref*c), row sum, running block max, bf16 pack -- all in registers: the MUFU-bound part
-      // of the block does not depend on the previous P V, so it runs while that MMA is still in flight
-      float rs0 = 0.f, rs1 = 0.f, bm0 = -INFINITY, bm1 = -INFINITY;
-      uint32_t packed[64];
+        ms = m_ref * scale_log2;
 #pragma unroll
-      for (int i = 0; i < 128; i += 2) {
-        const float s0 = __uint_as_float(sr[i]), s1 = __uint_as_float(sr[i + 1]);
-        const float p0 = fast_exp2(fmaf(s0, scale_log2, -ms));
-        const float p1 = fast_exp2(fmaf(s1, scale_log2, -ms));
-        rs0 += p0;
-        rs1 += p1;
-        bm0 = fmaxf(bm0, s0);
-        bm1 = fmaxf(bm1, s1);
-        packed[i >> 1] = pack2(p0, p1);
+        for (int c = 0; c < kChunks; ++c) exp_chunk(sr + c * 32, c);
+      } else {
+        // later blocks exponentiate against the inherited reference: TMEM reads (64 B/clk/SM, as scarce as the
+        // MUFU) are software-pipelined chunk by chunk under the exp work instead of being a serial pre-pass
+        ms = m_ref * scale_log2;
+        uint32_t rbuf[2][32];
+        ptx::tmem_ld_32x32b_x32(t_s + 0, rbuf[0]);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          if (c + 1 < kChunks) ptx::tmem_ld_32x32b_x32(t_s + (c + 1) * 32, rbuf[(c + 1) & 1]);
+          if (c + 1 == kChunks) {
+            // S_j fully read -> the MMA warp may overwrite it with S_{j+1}
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(s_free));
+          }
+          exp_chunk(rbuf[c & 1], c);
+          if (c + 1 < kChunks) ptx::tmem_ld_wait();
+        }
       }
+      ATT_STAMP(3 + j * 5);
       // the previous P V must have consumed P (smem) and updated O before we touch either
       if (j > 0) {
         ptx::mbar_wait(ptx::smem_u32(o_done), (j - 1) & 1);
         ptx::tc_fence_after();
       }
+      ATT_STAMP(4 + j * 5);
       if (pending) {   // warp-uniform
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
@@ -247,9 +296,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         tmem_st_wait();
         pending = false;
       }
-      // swizzled store of P (K-major SW128: 16-byte chunk index ^ (row & 7))
+      // swizzled store of P (K-major SW128: 16-byte chunk index ^ (row & 7)); one 16 KB atom per 64 keys
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < kChunks; ++c) {
         uint8_t* atom = s_p + (c >> 1) * kTileBytes + row * 128;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -264,6 +313,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(p_ready));
+      ATT_STAMP(5 + j * 5);
       // move the reference if some row of this warp outgrew it (decision is warp-uniform so the TMEM round trip
       // above stays convergent); applied before the next block's P V
       const float bmax = fmaxf(bm0, bm1);
@@ -297,6 +347,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       }
     }
   }
+  ATT_STAMP(31);
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -320,13 +371,13 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// tokens of one image: [N][ld] bf16 -> 3-D map {ld, N, B}, box {64, 128, 1}: rows past N are zero-filled
-static int make_map(CUtensorMap* m, const void* base, long long ld, int cols, int N, int B) {
+// tokens of one image: [N][ld] bf16 -> 3-D map {cols, N, B}, box {64, box_rows, 1}: rows past N are zero-filled
+static int make_map(CUtensorMap* m, const void* base, long long ld, int cols, int N, int B, int box_rows) {
   EncodeTiledFn fn = get_encode();
   if (!fn) { set_error("cuTensorMapEncodeTiled unavailable"); return D3R_ERR_CUDA; }
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)N, (cuuint64_t)B};
   cuuint64_t str[2] = {(cuuint64_t)ld * 2, (cuuint64_t)N * ld * 2};
-  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -338,6 +389,12 @@ static int make_map(CUtensorMap* m, const void* base, long long ld, int cols, in
 
 // q/k/v may be column slices of wider matrices (fused qkv / kv buffers): the map covers the whole matrix that
 // starts at the 16-byte aligned `*_base` pointer, the head column offset is added in the kernel.
+int attention_set_debug(void* dev_buf) {
+  unsigned long long* p = reinterpret_cast<unsigned long long*>(dev_buf);
+  D3R_CUDA(cudaMemcpyToSymbol(tc::g_attn_dbg, &p, sizeof(p)));
+  return D3R_OK;
+}
+
 int attention_hd64_tc(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
                       long long ldo, int B, int heads, int Nq, int Nk, float scale, cudaStream_t st) {
   D3R_CHECK_ARG(q && k && v && out && B > 0 && heads > 0 && Nq > 0 && Nk > 0, "attention: bad arguments");
@@ -346,9 +403,9 @@ int attention_hd64_tc(const void* q, long long ldq, const void* k, long long ldk
                 "attention: pointers must be 16-byte aligned");
   CUtensorMap mq, mk, mv;
   int rc;
-  if ((rc = tc::make_map(&mq, q, ldq, heads * 64, Nq, B))) return rc;
-  if ((rc = tc::make_map(&mk, k, ldk, heads * 64, Nk, B))) return rc;
-  if ((rc = tc::make_map(&mv, v, ldv, heads * 64, Nk, B))) return rc;
+  if ((rc = tc::make_map(&mq, q, ldq, heads * 64, Nq, B, tc::BQ))) return rc;
+  if ((rc = tc::make_map(&mk, k, ldk, heads * 64, Nk, B, tc::BK))) return rc;
+  if ((rc = tc::make_map(&mv, v, ldv, heads * 64, Nk, B, tc::BK))) return rc;
   static bool attr = false;
   if (!attr) {
     D3R_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));

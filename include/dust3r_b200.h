@@ -183,6 +183,9 @@ int d3r_attention_hd64(const void* q_dev, int64_t ldq, const void* k_dev, int64_
  * 2 (default) = CTA-pair kernels for long-K problems (>= 16 k-blocks of 64), 1-CTA otherwise. */
 void d3r_set_gemm_impl(int32_t impl);
 
+/* Debug aid: per-image timeline stamps (64 x uint64 %globaltimer per traced CTA) of the tcgen05 attention. */
+int d3r_attention_set_debug(void* dev_buf);
+
 /* Selects the attention kernel: 0 = mma.sync streaming kernel, 1 = tcgen05/TMEM kernel. */
 void d3r_set_attention_impl(int32_t impl);
 
