@@ -18,6 +18,7 @@
 #include "elementwise.h"
 #include "prof.h"
 #include <mutex>
+#include <type_traits>
 
 namespace d3r {
 namespace attn {
@@ -76,7 +77,8 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-#define ATT_STAMP(slot) do { if (dbg && (slot) < 32) dbg[(slot)] = gtime(); } while (0)
+#define ATT_STAMP(slot) do { if (dbg && (slot) < 16) dbg[(slot)] = gtime(); } while (0)
+#define ATT_CLK(k) do { if (dbg && threadIdx.x == 64 && j == 3) dbg[16 + (k)] = (unsigned long long)clock64(); } while (0)
 
 __global__ void __launch_bounds__(kThreads, kCTAsPerSM)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -213,6 +215,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     for (int j = 0; j < nblk; ++j) {
       const int nvalid = min(BK, Nk - j * BK);
       ATT_STAMP(1 + j * 5);
+      ATT_CLK(0);
       ptx::mbar_wait(ptx::smem_u32(s_ready), j & 1);
       ptx::tc_fence_after();
       ATT_STAMP(2 + j * 5);
@@ -221,11 +224,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       float ms;
       // p = exp2(s*c - m_ref*c), row sum, running block max, bf16 pack -- all in registers: the MUFU-bound part of
       // the block does not depend on the previous P V, so it runs while that MMA is still in flight.
-      auto exp_chunk = [&](const uint32_t* r, int c) {
+      // `masked` is a compile-time tag: only the ragged last key block pays for the per-element masking
+      auto exp_chunk_t = [&](const uint32_t* r, int c, auto masked) {
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           float s0 = __uint_as_float(r[i]), s1 = __uint_as_float(r[i + 1]);
-          if (nvalid < BK) {   // ragged last key block: masked keys contribute p = 0
+          if constexpr (decltype(masked)::value) {   // masked keys contribute p = 0
             if (c * 32 + i >= nvalid) s0 = -INFINITY;
             if (c * 32 + i + 1 >= nvalid) s1 = -INFINITY;
           }
@@ -237,6 +241,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           bm1 = fmaxf(bm1, s1);
           packed[c * 16 + (i >> 1)] = pack2(p0, p1);
         }
+      };
+      const bool ragged = nvalid < BK;   // warp-uniform
+      auto exp_chunk = [&](const uint32_t* r, int c) {
+        if (ragged) exp_chunk_t(r, c, std::true_type{});
+        else exp_chunk_t(r, c, std::false_type{});
       };
       constexpr int kChunks = BK / 32;
       if (j == 0) {
@@ -261,8 +270,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         // MUFU) are software-pipelined chunk by chunk under the exp work instead of being a serial pre-pass
         ms = m_ref * scale_log2;
         uint32_t rbuf[2][32];
+        ATT_CLK(1);
         ptx::tmem_ld_32x32b_x32(t_s + 0, rbuf[0]);
         ptx::tmem_ld_wait();
+        ATT_CLK(2);
 #pragma unroll
         for (int c = 0; c < kChunks; ++c) {
           if (c + 1 < kChunks) ptx::tmem_ld_32x32b_x32(t_s + (c + 1) * 32, rbuf[(c + 1) & 1]);
@@ -273,16 +284,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(s_free));
           }
           exp_chunk(rbuf[c & 1], c);
+          ATT_CLK(3 + c);
           if (c + 1 < kChunks) ptx::tmem_ld_wait();
         }
       }
       ATT_STAMP(3 + j * 5);
+      ATT_CLK(5);
       // the previous P V must have consumed P (smem) and updated O before we touch either
       if (j > 0) {
         ptx::mbar_wait(ptx::smem_u32(o_done), (j - 1) & 1);
         ptx::tc_fence_after();
       }
       ATT_STAMP(4 + j * 5);
+      ATT_CLK(6);
       if (pending) {   // warp-uniform
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
@@ -307,12 +321,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
               make_uint4(packed[c * 16 + 4 * q], packed[c * 16 + 4 * q + 1], packed[c * 16 + 4 * q + 2], packed[c * 16 + 4 * q + 3]);
         }
       }
+      ATT_CLK(7);
       l += rs0 + rs1;
       // make the generic-proxy smem writes of P visible to the tensor core (async proxy), then publish
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(p_ready));
+      ATT_CLK(8);
       ATT_STAMP(5 + j * 5);
       // move the reference if some row of this warp outgrew it (decision is warp-uniform so the TMEM round trip
       // above stays convergent); applied before the next block's P V

@@ -25,7 +25,9 @@ for z in (20, 40):
     sm, mm = t[z, :32], t[z, 32:]
     t0 = sm[0]
     print(f'--- image {z}: CTA start 0, end {(sm[31]-t0)/1e3:.2f} us')
-    for j in range(6):
+    clk = sm[16:25]
+    print('  block-3 softmax cycle deltas [wait_s, ld0, exp0, exp1, (o_done wait), (rescale), STS, fence+arrive]:', [int(clk[k+1]-clk[k]) for k in range(8)])
+    for j in range(2):
         a = [(sm[1 + j * 5 + k] - t0) / 1e3 for k in range(5)]
         m = [(mm[1 + j * 3 + k] - t0) / 1e3 for k in range(3)]
         print(f' blk {j}: softmax wait_s {a[0]:.2f} got_s {a[1]:.2f} exps_done {a[2]:.2f} o_done {a[3]:.2f} p_ready {a[4]:.2f} | mma S_issued {m[0]:.2f} p_seen {m[1]:.2f} PV_issued {m[2]:.2f}')
