@@ -176,6 +176,10 @@ def run_reference_arm(args):
     from dust3r_b200.config import vitl_512_dpt
     from dust3r_b200.utils.synth import synth_state_dict, synth_images
     from oracle.forward_oracle import forward_oracle
+    try:                                   # torchrun exports OMP_NUM_THREADS=1: take every host core this process may use
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except (AttributeError, RuntimeError):
+        torch.set_num_threads(os.cpu_count() or 1)
     cfg = vitl_512_dpt()
     sd = synth_state_dict(cfg, seed=0)
     imgs = synth_images(2, H, W, seed=3)

@@ -49,6 +49,8 @@ def _declare(lib):
     lib.d3r_prof_enable.argtypes = [C.c_int]
     lib.d3r_prof_report.restype = C.c_int
     lib.d3r_prof_report.argtypes = [C.c_char_p, C.c_int]
+    lib.d3r_prof_dump.restype = C.c_int
+    lib.d3r_prof_dump.argtypes = [C.c_char_p, C.c_int]
     lib.d3r_sizeof_align_desc.restype = C.c_int
     lib.d3r_align_workspace_floats.restype = i64
     lib.d3r_align_workspace_floats.argtypes = [i32, i32, i32, i32]
@@ -126,4 +128,14 @@ def prof_report():
     n = get_lib().d3r_prof_report(buf, len(buf))
     if n < 0:
         raise D3RError('profile report does not fit the buffer')
+    return json.loads(buf.value.decode())
+
+
+def prof_dump():
+    """Every launch recorded since prof_enable(True): [{tag, detail, ms, flops, bytes}] in launch order."""
+    import json
+    buf = C.create_string_buffer(1 << 22)
+    n = get_lib().d3r_prof_dump(buf, len(buf))
+    if n < 0:
+        raise D3RError('profile dump does not fit the buffer')
     return json.loads(buf.value.decode())

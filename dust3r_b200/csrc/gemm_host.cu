@@ -26,14 +26,14 @@ static EncodeTiledFn get_encode() {
 }
 
 static int encode(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                  const cuuint32_t* box) {
+                  const cuuint32_t* box, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
   EncodeTiledFn fn = get_encode();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
     return D3R_ERR_CUDA;
   }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box,
+  CUresult r = fn(m, dtype, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -54,35 +54,39 @@ int pick_block_n(int N, uint32_t flags) {
   return (N > 128) ? 256 : 128;
 }
 
-template <int BN>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int total_tiles, cudaStream_t st) {
+template <int BN, int EPI>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const Params& p, int total_tiles, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    D3R_CUDA(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes));
+    D3R_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, EPI>::kSmemBytes));
     attr_set = true;
   }
   int grid = total_tiles < num_sms() ? total_tiles : num_sms();
   const char* tag = (p.mode == 1) ? ((p.flags & F_HEAD_FINAL) ? "conv3x3_head_tail" : "conv3x3_tcgen05")
                                   : (BN == 256 ? "gemm_tcgen05_bn256" : (BN == 128 ? "gemm_tcgen05_bn128" : "gemm_tcgen05_bn64"));
-  prof::Scope scope(tag, st, 2.0 * double(p.M) * double(p.N) * double(p.K));
-  gemm_kernel<BN><<<grid, kNumThreads, Cfg<BN>::kSmemBytes, st>>>(ta, tb, p);
+  char detail[96];
+  snprintf(detail, sizeof(detail), "M=%d N=%d K=%d flags=0x%x mode=%d epi=%d", p.M, p.N, p.K, (unsigned)p.flags, p.mode, EPI);
+  prof::Scope scope(tag, st, 2.0 * double(p.M) * double(p.N) * double(p.K), 0.0, 1, detail);
+  gemm_kernel<BN, EPI><<<grid, kNumThreads, Cfg<BN, EPI>::kSmemBytes, st>>>(ta, tb, to, p);
   D3R_LAUNCH_CHECK();
   return D3R_OK;
 }
 
 // 0: 1-CTA kernels, 1: CTA-pair (cta_group::2) kernels whenever BLOCK_N >= 128, 2 (default): pair kernels when
-// the mainloop is long enough to dominate the tile (>= 16 k-blocks, i.e. K >= 1024: every encoder GEMM, fc2 of
-// the decoder, the 3x3 convolutions), 1-CTA kernels for the short-K decoder projections which stay
-// epilogue-bound (measured: profiles/r01_gemm_impl_compare*.jsonl)
+// the mainloop is long enough to dominate the tile (>= g_pair_min_kb k-blocks), 1-CTA kernels for the short-K
+// decoder projections (measured: profiles/r01_gemm_impl_compare*.jsonl)
 static int g_impl = 2;
+static int g_pair_min_kb = 16;
 void set_impl(int impl) { g_impl = impl; }
-bool use_pair(int bn, int num_kb) { return bn >= 128 && (g_impl == 1 || (g_impl == 2 && num_kb >= 16)); }
+void set_pair_min_kb(int kb) { g_pair_min_kb = kb; }
+bool use_pair(int bn, int num_kb) { return bn >= 128 && (g_impl == 1 || (g_impl == 2 && num_kb >= g_pair_min_kb)); }
 
-template <int BN>
-static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int m_tiles, int n_tiles, cudaStream_t st) {
+template <int BN, int EPI>
+static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const Params& p, int m_tiles, int n_tiles,
+                   cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    D3R_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN>::kSmemBytes));
+    D3R_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN, EPI>::kSmemBytes));
     attr_set = true;
   }
   const int cluster_tiles = ((m_tiles + 1) / 2) * n_tiles;
@@ -90,23 +94,52 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p
   const int clusters = cluster_tiles < max_clusters ? cluster_tiles : max_clusters;
   const char* tag = (p.mode == 1) ? ((p.flags & F_HEAD_FINAL) ? "conv3x3_head_tail_2cta" : "conv3x3_tcgen05_2cta")
                                   : (BN == 256 ? "gemm_tcgen05_2cta_bn256" : "gemm_tcgen05_2cta_bn128");
-  prof::Scope scope(tag, st, 2.0 * double(p.M) * double(p.N) * double(p.K));
-  gemm2_kernel<BN><<<2 * clusters, kNumThreads, Cfg2<BN>::kSmemBytes, st>>>(ta, tb, p);
+  char detail[96];
+  snprintf(detail, sizeof(detail), "M=%d N=%d K=%d flags=0x%x mode=%d epi=%d", p.M, p.N, p.K, (unsigned)p.flags, p.mode, EPI);
+  prof::Scope scope(tag, st, 2.0 * double(p.M) * double(p.N) * double(p.K), 0.0, 1, detail);
+  gemm2_kernel<BN, EPI><<<2 * clusters, kNumThreads, Cfg2<BN, EPI>::kSmemBytes, st>>>(ta, tb, to, p);
   D3R_LAUNCH_CHECK();
   return D3R_OK;
 }
 
 static int dispatch(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int total_tiles, cudaStream_t st) {
+  // epilogue specialisation (BLOCK_N = 256 only: every hot projection of the two ViTs has N % 256 == 0)
+  int epi = (bn == 256) ? pick_epi(p.mode, p.flags) : EPI_GENERIC;
+  CUtensorMap to = ta;   // placeholder unless the epilogue stores through TMA
+  if (epi == EPI_RESID) {
+    if ((reinterpret_cast<uintptr_t>(p.out) & 15) != 0 || p.ldo % 4 != 0) {
+      epi = EPI_GENERIC;   // TMA needs 16-byte aligned rows; the register epilogue has no such requirement
+    } else {
+      cuuint64_t dims[2] = {(cuuint64_t)p.N, (cuuint64_t)p.M};
+      cuuint64_t str[1] = {(cuuint64_t)p.ldo * 4};
+      cuuint32_t box[2] = {32, 32};
+      int rc = encode(&to, p.out, 2, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+      if (rc) return rc;
+    }
+  }
   if (use_pair(bn, p.num_kb)) {
     const int n_tiles = (p.N + bn - 1) / bn;
     const int m_tiles = total_tiles / n_tiles;
-    if (bn == 256) return launch2<256>(ta, tb, p, m_tiles, n_tiles, st);
-    return launch2<128>(ta, tb, p, m_tiles, n_tiles, st);
+    if (bn == 256) {
+      switch (epi) {
+        case EPI_RESID: return launch2<256, EPI_RESID>(ta, tb, to, p, m_tiles, n_tiles, st);
+        case EPI_ACT: return launch2<256, EPI_ACT>(ta, tb, to, p, m_tiles, n_tiles, st);
+        case EPI_ROPE: return launch2<256, EPI_ROPE>(ta, tb, to, p, m_tiles, n_tiles, st);
+        default: return launch2<256, EPI_GENERIC>(ta, tb, to, p, m_tiles, n_tiles, st);
+      }
+    }
+    return launch2<128, EPI_GENERIC>(ta, tb, to, p, m_tiles, n_tiles, st);
   }
   switch (bn) {
-    case 256: return launch<256>(ta, tb, p, total_tiles, st);
-    case 128: return launch<128>(ta, tb, p, total_tiles, st);
-    case 64: return launch<64>(ta, tb, p, total_tiles, st);
+    case 256:
+      switch (epi) {
+        case EPI_RESID: return launch<256, EPI_RESID>(ta, tb, to, p, total_tiles, st);
+        case EPI_ACT: return launch<256, EPI_ACT>(ta, tb, to, p, total_tiles, st);
+        case EPI_ROPE: return launch<256, EPI_ROPE>(ta, tb, to, p, total_tiles, st);
+        default: return launch<256, EPI_GENERIC>(ta, tb, to, p, total_tiles, st);
+      }
+    case 128: return launch<128, EPI_GENERIC>(ta, tb, to, p, total_tiles, st);
+    case 64: return launch<64, EPI_GENERIC>(ta, tb, to, p, total_tiles, st);
   }
   set_error("unsupported BLOCK_N %d", bn);
   return D3R_ERR_INVALID;
@@ -182,6 +215,7 @@ int conv3x3_bf16(const void* x_nhwc, const void* w_packed, int B, int H, int W, 
 using namespace d3r;
 
 extern "C" void d3r_set_gemm_impl(int32_t impl) { gemm::set_impl(impl); }
+extern "C" void d3r_set_gemm_pair_min_kblocks(int32_t kb) { gemm::set_pair_min_kb(kb); }
 
 extern "C" int d3r_gemm_bf16(const void* A, const void* B, void* out, const float* bias, const void* add0, void* out2,
                              int32_t M, int32_t N, int32_t K, int64_t ldo, uint32_t flags, const float* rope_cos,

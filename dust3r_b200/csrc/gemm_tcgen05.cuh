@@ -75,27 +75,56 @@ struct Params {
   float conf_min, conf_max;
 };
 
-template <int BLOCK_N>
+// Epilogue specialisations (compile-time): the runtime flag word is masked with the set a specialisation supports,
+// so the other epilogue branches are dead code and do not cost registers or instruction cache.
+//   EPI_GENERIC  every flag (conv, transposed conv, DPT fusions, head tail, ...)
+//   EPI_RESID    out(f32) += acc + bias  through shared memory and a TMA reduce-add (cp.reduce.async.bulk.tensor):
+//                the residual stream is never loaded by the SM and is updated in whole 128-byte lines
+//   EPI_ACT      bias / GELU / ReLU -> bf16
+//   EPI_ROPE     bias + 2D RoPE -> bf16 (q,k,v projections)
+enum : int { EPI_GENERIC = 0, EPI_RESID = 1, EPI_ACT = 2, EPI_ROPE = 3 };
+template <int EPI> struct EpiMask { static constexpr uint32_t value = 0xFFFFFFFFu; };
+template <> struct EpiMask<EPI_RESID> { static constexpr uint32_t value = F_BIAS | F_RESID_INPLACE; };
+template <> struct EpiMask<EPI_ACT> { static constexpr uint32_t value = F_BIAS | F_GELU | F_RELU; };
+template <> struct EpiMask<EPI_ROPE> { static constexpr uint32_t value = F_BIAS | F_ROPE; };
+__host__ __device__ inline int pick_epi(int mode, uint32_t flags) {
+  if (mode != 0) return EPI_GENERIC;
+  if ((flags & ~F_BIAS) == F_RESID_INPLACE) return EPI_RESID;
+  if ((flags & ~EpiMask<EPI_ACT>::value) == 0) return EPI_ACT;
+  if ((flags & ~EpiMask<EPI_ROPE>::value) == 0) return EPI_ROPE;
+  return EPI_GENERIC;
+}
+constexpr int kOutStageBytes = 32 * 32 * 4;   // one 32-row x 32-column fp32 box per epilogue warp (EPI_RESID)
+
+template <int BLOCK_N, int EPI = EPI_GENERIC>
 struct Cfg {
   static constexpr int kStageA = BLOCK_M * BLOCK_K * 2;
   static constexpr int kStageB = BLOCK_N * BLOCK_K * 2;
-  static constexpr int kStages = (BLOCK_N >= 256) ? 4 : ((BLOCK_N >= 128) ? 6 : 8);
+  static constexpr int kOutStage = (EPI == EPI_RESID) ? kNumEpilogueWarps * kOutStageBytes : 0;
+  static constexpr int kStages = ((BLOCK_N >= 256) ? 4 : ((BLOCK_N >= 128) ? 6 : 8)) - ((EPI == EPI_RESID) ? 1 : 0);
   static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                                    : (2 * BLOCK_N <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * (kStageA + kStageB) + 1024 /*align*/ + 256 /*barriers*/ + 4 * 128 * 4 + 64;
+  static constexpr int kSmemBytes = kStages * (kStageA + kStageB) + kOutStage + 1024 /*align*/ + 256 /*barriers*/ + 4 * 128 * 4 + 64 +
+                                    kNumEpilogueWarps * 128 * 4 /*bias slices*/;
 };
 
 // exact-erf GELU (nn.GELU default).  erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the
-// bf16 rounding of the stored activation); ~3x fewer instructions than erff() in the epilogue hot loop.
+// bf16 rounding of the stored activation).  Written for the epilogue's instruction budget (14 per element, two
+// of them MUFU): with u = |x| sqrt(log2(e)/2),  exp(-x^2/2) = 2^(-u u);  h = x/2 poly(t) t 2^(-u u) (the 1/2 is
+// folded into the coefficients) is x/2 (1 - erf(|x|/sqrt2)), and  gelu(x) = max(x, 0) - |h|  on both sides of 0.
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float e = 1.f - poly * t * __expf(-z * z);   // erf(|x|/sqrt2)
-  return 0.5f * x * (1.f + copysignf(e, x));
+  constexpr float kU = 0.84932180028801904f;            // sqrt(log2(e) / 2)
+  constexpr float kP = 0.3275911f * 0.70710678118654752f / kU;
+  const float u = fabsf(x) * kU;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(kP, u, 1.f)));
+  float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-u * u));
+  const float h = x * (poly * t * e);
+  return fmaxf(x, 0.f) - fabsf(h);
 }
 
 // 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): a lane moves one whole 32-byte sector per instruction,
@@ -118,22 +147,25 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(kNumThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
-  using C = Cfg<BLOCK_N>;
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const __grid_constant__ CUtensorMap tmap_o, const Params p) {
+  using C = Cfg<BLOCK_N, EPI>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + C::kStages * C::kStageA;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * (C::kStageA + C::kStageB));
+  uint8_t* smem_out = smem + C::kStages * (C::kStageA + C::kStageB);   // EPI_RESID: [kNumEpilogueWarps][32 rows][128 B], 128B-swizzled
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + C::kOutStage);
   uint64_t* full_bar = bars;                      // [kStages]
   uint64_t* empty_bar = bars + C::kStages;        // [kStages]
   uint64_t* tfull_bar = bars + 2 * C::kStages;    // [2]
   uint64_t* tempty_bar = bars + 2 * C::kStages + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
   float* s_w4 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [4][128] + [4]
+  float* s_bias = s_w4 + 4 * 128 + 16;                                             // [kNumEpilogueWarps][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
@@ -242,7 +274,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int ch_end = whole_row ? (half == 0 ? kChunks : 0) : (half + 1) * (kChunks / 2);
     int acc = 0;
     uint32_t acc_phase = 0;
-    const uint32_t flags = p.flags;
+    const uint32_t flags = p.flags & EpiMask<EPI>::value;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int tn = tile % n_tiles, tm = tile / n_tiles;
       // ---- where does this thread's row live in the output? ----
@@ -273,12 +305,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
       float head_acc[4] = {0.f, 0.f, 0.f, 0.f};
 
+      // ---- work that does not need the accumulator, issued before waiting for it ----
+      // (a) this warp's bias slice -> shared memory (one coalesced load per tile instead of 8 dependent
+      //     broadcast loads per 32-column chunk on the epilogue's critical path)
+      float* s_bias_w = s_bias + (warp - 2) * 128;
+      if (flags & F_BIAS) {
+        __syncwarp();
+        for (int i = lane * 4; i < (ch_end - ch_begin) * 32; i += 128) {
+          const int c = tn * BLOCK_N + ch_begin * 32 + i;
+          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + ((flags & F_CONVT) ? (c % p.tCout) : c)));
+          *reinterpret_cast<float4*>(s_bias_w + i) = b;
+        }
+        __syncwarp();
+      }
       ptx::mbar_wait(ptx::smem_u32(&tfull_bar[acc]), acc_phase);
       ptx::tc_fence_after();
-#pragma unroll 1
-      for (int ch = ch_begin; ch < ch_end; ++ch) {
+      // one 32-column chunk; false = past the last column (warp-uniform)
+      auto chunk_body = [&](const int ch) -> bool {
         const int col0 = tn * BLOCK_N + ch * 32;
-        if (col0 >= p.N) break;  // warp-uniform
+        if (col0 >= p.N) return false;
         uint32_t raw[32];
         ptx::tmem_ld_32x32b_x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BLOCK_N + ch * 32), raw);
         ptx::tmem_ld_wait();
@@ -286,13 +332,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
         if (flags & F_BIAS) {
-          const int bcol = (flags & F_CONVT) ? (col0 % p.tCout) : col0;
-          const float4* b4p = reinterpret_cast<const float4*>(p.bias + bcol);
+          const float4* b4p = reinterpret_cast<const float4*>(s_bias_w + (ch - ch_begin) * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(b4p + j);
+            const float4 b = b4p[j];
             v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
           }
+        }
+        if constexpr (EPI == EPI_RESID) {
+          // thread = row: 8 x 16 B into this warp's 128B-swizzled staging box, then one TMA reduce-add of the
+          // 32 x 32 box onto the fp32 residual stream (rows past M are clipped by the tensor map)
+          uint8_t* stg = smem_out + (warp - 2) * kOutStageBytes;
+          if (lane == 0) ptx::bulk_wait_read0();   // the previous box has left shared memory
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_reduce_add_2d(&tmap_o, ptx::smem_u32(stg), col0, tm * BLOCK_M + quarter * 32);
+            ptx::bulk_commit();
+          }
+          return true;
         }
         if (flags & F_GELU) {
 #pragma unroll
@@ -326,9 +388,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             head_acc[2] += r * s_w4[2 * 128 + c];
             head_acc[3] += r * s_w4[3 * 128 + c];
           }
-          continue;
+          return true;
         }
-        if (!valid) continue;
+        if (!valid) return true;
         long long off;
         if (flags & F_CONVT) {
           const int kk = col0 / p.tCout, co = col0 - kk * p.tCout;
@@ -417,7 +479,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             }
           }
         }
-      }
+        return true;
+      };
+#pragma unroll 1
+      for (int ch = ch_begin; ch < ch_end; ++ch)
+        if (!chunk_body(ch)) break;
       // accumulator drained: hand the TMEM buffer back to the MMA warp
       ptx::tc_fence_before();
       __syncwarp();
@@ -447,6 +513,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
   }
 
+  if constexpr (EPI == EPI_RESID) {
+    if (warp >= 2 && lane == 0) ptx::bulk_wait0();   // staged boxes fully written before shared memory goes away
+  }
   // ---- teardown ----
   ptx::tc_fence_before();
   __syncthreads();

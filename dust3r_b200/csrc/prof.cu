@@ -11,14 +11,14 @@ namespace prof {
 
 static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_enabled{0};
-struct Rec { const char* tag; cudaEvent_t a, b; double flops, bytes; int launches; };
+struct Rec { const char* tag; cudaEvent_t a, b; double flops, bytes; int launches; std::string detail; };
 static std::vector<Rec> g_recs;
 static std::mutex g_mu;
 
-Scope::Scope(const char* tag, cudaStream_t s, double flops, double bytes, int launches) : idx(-1), st(s) {
+Scope::Scope(const char* tag, cudaStream_t s, double flops, double bytes, int launches, const char* detail) : idx(-1), st(s) {
   g_launches.fetch_add(launches, std::memory_order_relaxed);
   if (!g_enabled.load(std::memory_order_relaxed)) return;
-  Rec r{tag, nullptr, nullptr, flops, bytes, launches};
+  Rec r{tag, nullptr, nullptr, flops, bytes, launches, detail ? detail : ""};
   cudaEventCreate(&r.a);
   cudaEventCreate(&r.b);
   cudaEventRecord(r.a, st);
@@ -66,6 +66,25 @@ extern "C" int d3r_prof_report(char* buf, int cap) {
     first = false;
   }
   s += "}";
+  if ((int)s.size() + 1 > cap) return -1;
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return (int)s.size();
+}
+extern "C" int d3r_prof_dump(char* buf, int cap) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  std::string s = "[";
+  bool first = true;
+  for (auto& r : g_recs) {
+    cudaEventSynchronize(r.b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    char tmp[384];
+    snprintf(tmp, sizeof(tmp), "%s{\"tag\": \"%s\", \"detail\": \"%s\", \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}", first ? "" : ", ",
+             r.tag, r.detail.c_str(), ms, r.flops, r.bytes);
+    s += tmp;
+    first = false;
+  }
+  s += "]";
   if ((int)s.size() + 1 > cap) return -1;
   memcpy(buf, s.c_str(), s.size() + 1);
   return (int)s.size();

@@ -44,6 +44,8 @@ long long d3r_launch_count(void);
 void d3r_launch_count_reset(void);
 void d3r_prof_enable(int on);
 int d3r_prof_report(char* buf, int cap);
+/* every recorded launch in order: JSON list [{tag, detail, ms, flops, bytes}] (length, or -1 if it does not fit) */
+int d3r_prof_dump(char* buf, int cap);
 
 /* ------------------------------------------------------------------------------------------
  * Path 2 — global alignment (replaces the body of global_alignment_iter(),
@@ -182,6 +184,8 @@ int d3r_attention_hd64(const void* q_dev, int64_t ldq, const void* k_dev, int64_
 /* Selects the GEMM / conv kernel family: 0 = 1-CTA tcgen05 kernels, 1 = CTA-pair (cta_group::2) kernels,
  * 2 (default) = CTA-pair kernels for long-K problems (>= 16 k-blocks of 64), 1-CTA otherwise. */
 void d3r_set_gemm_impl(int32_t impl);
+/* Tuning aid for impl 2: minimum number of 64-wide k-blocks for which the CTA-pair kernel is used (default 16). */
+void d3r_set_gemm_pair_min_kblocks(int32_t kblocks);
 
 /* Debug aid: per-image timeline stamps (64 x uint64 %globaltimer per traced CTA) of the tcgen05 attention. */
 int d3r_attention_set_debug(void* dev_buf);
