@@ -17,7 +17,7 @@
 #include "sm100_ptx.cuh"
 #include "elementwise.h"
 #include "prof.h"
-#include <mutex>
+#include "attention_tc_common.cuh"
 #include <type_traits>
 
 namespace d3r {
@@ -35,40 +35,7 @@ constexpr int kSmemBytes = kTileBytes /*Q*/ + 2 * kKVBytes /*K ring*/ + 2 * kKVB
 constexpr int kTmemCols = (BK + 64 <= 128) ? 128 : 256;
 constexpr uint32_t kColS = 0, kColO = BK;
 
-__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
-      "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
-      "r"(r[30]), "r"(r[31])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// MN-major (N contiguous) 128B-swizzled B operand: rows of the smem tile are K (keys), 128 B each = 64 N values.
-// 8-key groups are 1024 B apart (stride byte offset); one 64-wide N atom only, so the leading offset is unused.
-__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= uint64_t((smem_addr & 0x3FFFF) >> 4);
-  d |= uint64_t(1024 >> 4) << 16;
-  d |= uint64_t(1024 >> 4) << 32;
-  d |= uint64_t(1) << 46;
-  d |= uint64_t(2) << 61;
-  return d;
-}
-
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ float fast_exp2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
+using namespace tcc;
 
 // optional timeline instrumentation (debug aid)
 __device__ unsigned long long* g_attn_dbg = nullptr;
@@ -372,40 +339,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  });
-  return fn;
-}
-
-// tokens of one image: [N][ld] bf16 -> 3-D map {cols, N, B}, box {64, box_rows, 1}: rows past N are zero-filled
-static int make_map(CUtensorMap* m, const void* base, long long ld, int cols, int N, int B, int box_rows) {
-  EncodeTiledFn fn = get_encode();
-  if (!fn) { set_error("cuTensorMapEncodeTiled unavailable"); return D3R_ERR_CUDA; }
-  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)N, (cuuint64_t)B};
-  cuuint64_t str[2] = {(cuuint64_t)ld * 2, (cuuint64_t)N * ld * 2};
-  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
-  cuuint32_t es[3] = {1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("attention: cuTensorMapEncodeTiled failed (%d)", (int)r); return D3R_ERR_CUDA; }
-  return D3R_OK;
-}
-
 }  // namespace tc
 
 // q/k/v may be column slices of wider matrices (fused qkv / kv buffers): the map covers the whole matrix that
 // starts at the 16-byte aligned `*_base` pointer, the head column offset is added in the kernel.
+int attention_tc2_set_debug(void* dev_buf);
 int attention_set_debug(void* dev_buf) {
+  if (int rc = attention_tc2_set_debug(dev_buf)) return rc;
   unsigned long long* p = reinterpret_cast<unsigned long long*>(dev_buf);
   D3R_CUDA(cudaMemcpyToSymbol(tc::g_attn_dbg, &p, sizeof(p)));
   return D3R_OK;

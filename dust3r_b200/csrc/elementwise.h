@@ -21,6 +21,8 @@ int attention_hd64(const void* q, long long ldq, const void* k, long long ldk, c
                    long long ldo, int B, int heads, int Nq, int Nk, float scale, cudaStream_t st);
 int attention_hd64_tc(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
                       long long ldo, int B, int heads, int Nq, int Nk, float scale, cudaStream_t st);
+int attention_hd64_tc2(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
+                      long long ldo, int B, int heads, int Nq, int Nk, float scale, cudaStream_t st);
 void set_impl(int impl);
 }  // namespace attn
 }  // namespace d3r

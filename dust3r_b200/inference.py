@@ -8,6 +8,8 @@ the predictions go through pinned staging buffers and overlap the next batch's c
 (SURVEY §8f rank 2)."""
 from __future__ import annotations
 
+import os
+
 import torch
 import tqdm
 
@@ -57,28 +59,58 @@ def check_if_same_size(pairs):
     return all(shapes1[0] == s for s in shapes1) and all(shapes2[0] == s for s in shapes2)
 
 
-def _collate_views_pinned(views, pin):
-    """collate_with_cat for a list of view dicts; image tensors are concatenated straight into pinned
-    host memory so the H2D copy can be asynchronous."""
-    out = {}
-    for k in views[0]:
-        vals = [v[k] for v in views]
-        if k == 'img' and pin:
-            n = sum(int(t.shape[0]) for t in vals)
-            buf = torch.empty((n,) + tuple(vals[0].shape[1:]), dtype=vals[0].dtype, pin_memory=True)
-            torch.cat(vals, out=buf)
-            out[k] = buf
-        else:
-            out[k] = collate_with_cat(vals)
-    return out
+_POOL = None
+_TRACE = None   # set to a list to collect (label, perf_counter) host timestamps of the pipeline (diagnostics)
+
+
+def _mark(label):
+    if _TRACE is not None:
+        import time
+        _TRACE.append((label, time.perf_counter()))
+
+
+def _copy_pool():
+    global _POOL
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) // 2)))
+    return _POOL
+
+
+def _fill_pinned(dst, tensors, row0, wait=True):
+    """Copy each view's image rows into the pinned staging tensor `dst` starting at row `row0` (memcpy on a small
+    thread pool: Tensor.copy_ releases the GIL, one thread saturates only ~10 GB/s of host bandwidth).
+    Returns (next row, futures); with wait=False the copies are left running in the background."""
+    jobs, r = [], row0
+    for t in tensors:
+        k = int(t.shape[0])
+        jobs.append((dst[r:r + k], t))
+        r += k
+    futs = [_copy_pool().submit(d.copy_, t) for d, t in jobs]
+    if wait:
+        for f in futs:
+            f.result()
+        futs = []
+    return r, futs
+
+
+def _micro_batch(batch_size):
+    """Pairs per fused forward call.  A user batch of >= 16 pairs is run as two halves so that the host-side
+    staging + H2D of one half and the D2H of the other overlap the GPU compute (per-pair results do not depend on
+    the batch they are computed in); halves stay even so symmetrised (a,b),(b,a) neighbours are kept together."""
+    if batch_size < 16:
+        return batch_size
+    half = (batch_size + 1) // 2
+    return half + (half & 1)
 
 
 @torch.no_grad()
 def inference(pairs, model, device, batch_size=8, verbose=True, keep_on_device=False):
     """inference.py:55-72.  Returns {'view1','view2','pred1','pred2','loss'}; tensors on CPU (pinned) unless
-    keep_on_device.  Per batch: pinned H2D of the images -> one fused forward -> predictions copied D2H on a
-    side stream into the final (whole pair list) pinned output, overlapping the next batch's compute.  The
-    returned views are the caller's own CPU tensors (the reference round-trips them through the GPU)."""
+    keep_on_device.  Software pipeline over micro-batches: images are gathered into pinned host memory (which is
+    also the returned, collated view), uploaded on a copy stream, run through one fused forward call, and the
+    predictions are copied D2H on a second side stream into the final (whole pair list) pinned output -- the
+    upload of batch k+1 and the download of batch k-1 overlap the compute of batch k."""
     if verbose:
         print(f'>> Inference with model on {len(pairs)} image pairs')
     multiple_shapes = not check_if_same_size(pairs)
@@ -94,35 +126,74 @@ def inference(pairs, model, device, batch_size=8, verbose=True, keep_on_device=F
             result.append(res if keep_on_device else to_cpu(res))
         return collate_with_cat(result, lists=multiple_shapes)
 
+    _mark('begin')
     n = len(pairs)
-    view1_all = collate_with_cat([a for a, b in pairs])
-    view2_all = collate_with_cat([b for a, b in pairs])
+    views = ([a for a, b in pairs], [b for a, b in pairs])
+    rows = [sum(int(v['img'].shape[0]) for v in vs) for vs in views]
+    assert rows[0] == rows[1], 'both views of a pair must hold the same number of images'
+    proto = [vs[0]['img'] for vs in views]
+    # pinned staging = the collated 'img' of the returned views; device copies of the whole pair list (a few MB / pair)
+    img_pin = [torch.empty((rows[k],) + tuple(proto[k].shape[1:]), dtype=proto[k].dtype, pin_memory=True) for k in range(2)]
+    img_dev = [torch.empty(img_pin[k].shape, dtype=img_pin[k].dtype, device=dev) for k in range(2)]
+    meta_all = [{key: collate_with_cat([v[key] for v in vs]) for key in vs[0] if key != 'img'} for vs in views]
+    _mark('alloc+meta')
     outs = None
     main = torch.cuda.current_stream(dev)
-    side = torch.cuda.Stream(device=dev)
-    for i in tqdm.trange(0, n, batch_size, disable=not verbose):
-        chunk = pairs[i:i + batch_size]
-        v1 = _collate_views_pinned([a for a, b in chunk], pin=True)
-        v2 = _collate_views_pinned([b for a, b in chunk], pin=True)
-        d1 = dict(v1, img=v1['img'].to(dev, non_blocking=True))
-        d2 = dict(v2, img=v2['img'].to(dev, non_blocking=True))
-        pred1, pred2 = model(d1, d2)
+    up, side = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    up.wait_stream(main)
+    mb = _micro_batch(batch_size)
+    r0 = 0
+    pending = []
+    for i in tqdm.trange(0, n, mb, disable=not verbose):
+        chunk = (views[0][i:i + mb], views[1][i:i + mb])
+        r1 = r0
+        srcs = [[v['img'] for v in chunk[k]] for k in range(2)]
+        direct = all(t.is_pinned() for ts in srcs for t in ts)
+        for k in range(2):
+            # sources already in pinned memory are uploaded straight from where they are; the collated copy that the
+            # caller gets back is then filled in the background, off the critical path
+            r1, futs = _fill_pinned(img_pin[k], srcs[k], r0, wait=not direct)
+            pending.extend(futs)
+        _mark('fill')
+        with torch.cuda.stream(up):
+            for k in range(2):
+                if direct:
+                    r = r0
+                    for t in srcs[k]:
+                        img_dev[k][r:r + int(t.shape[0])].copy_(t, non_blocking=True)
+                        r += int(t.shape[0])
+                else:
+                    img_dev[k][r0:r1].copy_(img_pin[k][r0:r1], non_blocking=True)
+        ev_up = torch.cuda.Event()
+        ev_up.record(up)
+        main.wait_event(ev_up)
+        d = [dict({key: collate_with_cat([v[key] for v in chunk[k]]) for key in chunk[k][0] if key != 'img'},
+                  img=img_dev[k][r0:r1]) for k in range(2)]
+        _mark('h2d+meta')
+        pred1, pred2 = model(d[0], d[1])
+        _mark('forward-enqueued')
         flat = {('pred1', k): v for k, v in pred1.items()}
         flat.update({('pred2', k): v for k, v in pred2.items()})
         if outs is None:
             if keep_on_device:
-                outs = {key: torch.empty((n,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev) for key, t in flat.items()}
+                outs = {key: torch.empty((rows[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=dev) for key, t in flat.items()}
             else:
-                outs = {key: torch.empty((n,) + tuple(t.shape[1:]), dtype=t.dtype, pin_memory=True) for key, t in flat.items()}
+                outs = {key: torch.empty((rows[0],) + tuple(t.shape[1:]), dtype=t.dtype, pin_memory=True) for key, t in flat.items()}
         ev = torch.cuda.Event()
         ev.record(main)
         with torch.cuda.stream(side):
             side.wait_event(ev)
             for key, t in flat.items():
-                outs[key][i:i + len(chunk)].copy_(t, non_blocking=True)
+                outs[key][r0:r1].copy_(t, non_blocking=True)
                 t.record_stream(side)
+        _mark('d2h-enqueued')
+        r0 = r1
     side.synchronize()
-    res = dict(view1=view1_all, view2=view2_all, pred1={}, pred2={}, loss=None)
+    for f in pending:
+        f.result()
+    _mark('synced')
+    main.wait_stream(up)
+    res = dict(view1=dict(meta_all[0], img=img_pin[0]), view2=dict(meta_all[1], img=img_pin[1]), pred1={}, pred2={}, loss=None)
     for (which, k), t in outs.items():
         res[which][k] = t
     return res

@@ -190,7 +190,8 @@ void d3r_set_gemm_pair_min_kblocks(int32_t kblocks);
 /* Debug aid: per-image timeline stamps (64 x uint64 %globaltimer per traced CTA) of the tcgen05 attention. */
 int d3r_attention_set_debug(void* dev_buf);
 
-/* Selects the attention kernel: 0 = mma.sync streaming kernel, 1 = tcgen05/TMEM kernel. */
+/* Selects the attention kernel: 0 = mma.sync streaming kernel, 1 = tcgen05/TMEM kernel (one thread per query row,
+ * 64-key blocks, 3 CTAs/SM), 2 (default) = tcgen05/TMEM split-row kernel (two warps per 32 rows, 128-key blocks). */
 void d3r_set_attention_impl(int32_t impl);
 
 /* ------------------------------------------------------------------------------------------
