@@ -143,7 +143,10 @@ def cloud_opt_section(device, pk, steps_iters=300):
                 config=dict(workload='8 synthetic views -> 28 pairs (symmetrize=False) at 512x384, PointCloudOptimizer, '
                                      '300 iters, lr 0.01 cosine, dist l1, conf log, init=None'),
                 ms_per_iter=ms / steps_iters, loss_first=float(losses[0]), loss_last=float(losses[-1]),
-                roofline=dict(bound='hbm', achieved=gbs, peak=pk['hbm'], unit='GB/s', frac=gbs / pk['hbm'], traffic=None,
+                roofline=dict(bound='hbm', achieved=gbs, peak=pk['hbm'], unit='GB/s', frac=gbs / pk['hbm'],
+                              # dram__bytes_read+write per align_iter launch, ncu --set full on this exact workload
+                              # (profiles/r01_prof_align_v11.raw.csv): 195.15 + 10.55 MB
+                              traffic=205.7e6, traffic_source='profiles/r01_prof_align_v11.raw.csv',
                               algorithmic_bytes_per_iter=by, peak_source=pk['source']),
                 e2e=dict(value=steps_iters / t_api, unit='iters/s', includes='H2D of 28 pairs of predictions, packing, 300 iters, loss readback',
                          final_loss=loss))
