@@ -351,6 +351,10 @@ int attention_set_debug(void* dev_buf) {
   return D3R_OK;
 }
 
+// debug: extra dynamic shared memory per CTA to lower the number of co-resident CTAs (occupancy scaling experiments)
+static int g_occupancy_pad = 0;
+void set_tc_occupancy_pad(int bytes) { g_occupancy_pad = bytes; }
+
 int attention_hd64_tc(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
                       long long ldo, int B, int heads, int Nq, int Nk, float scale, cudaStream_t st) {
   D3R_CHECK_ARG(q && k && v && out && B > 0 && heads > 0 && Nq > 0 && Nk > 0, "attention: bad arguments");
@@ -364,14 +368,14 @@ int attention_hd64_tc(const void* q, long long ldq, const void* k, long long ldk
   if ((rc = tc::make_map(&mv, v, ldv, heads * 64, Nk, B, tc::BK))) return rc;
   static bool attr = false;
   if (!attr) {
-    D3R_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+    D3R_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     // two CTAs per SM only fit with the maximum shared-memory carve-out
     D3R_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr = true;
   }
   dim3 grid((Nq + tc::BQ - 1) / tc::BQ, heads, B);
   prof::Scope scope("attention_tcgen05", st, 4.0 * double(B) * heads * double(Nq) * double(Nk) * 64.0);
-  tc::attention_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>(mq, mk, mv, (__nv_bfloat16*)out, ldo, Nq, Nk, 0, 0, 0,
+  tc::attention_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes + g_occupancy_pad, st>>>(mq, mk, mv, (__nv_bfloat16*)out, ldo, Nq, Nk, 0, 0, 0,
                                                                      scale * 1.4426950408889634f);
   D3R_LAUNCH_CHECK();
   return D3R_OK;

@@ -10,13 +10,13 @@ for (B, Hh, N) in [(64, 16, 768), (32, 12, 768)]:
     qkv = torch.randn((B, N, ld), device='cuda').bfloat16()
     out = torch.empty((B, N, Hh * 64), device='cuda', dtype=torch.bfloat16)
     res = {}
-    for impl in (1, 2, 42, 52, 62, 72):
+    for impl in (1, 31, 41, 2):   # impl 1 with 3 / 2 / 1 CTAs per SM (shared-memory padding), impl 2
         lib.d3r_set_attention_impl(impl)
         def f():
             _lib.check(lib.d3r_attention_hd64(qkv.data_ptr(), ld, qkv.data_ptr() + Hh * 128, ld, qkv.data_ptr() + Hh * 256, ld,
                                               out.data_ptr(), Hh * 64, B, Hh, N, N, 0.125, _lib.stream_ptr()))
         ms = timeit(f, warm=3, rep=20)
-        if impl in (1, 2, 72): res[impl] = out.float().clone()
+        if impl in (1, 2): res[impl] = out.float().clone()
         print(json.dumps(dict(kind='attention', impl=impl, B=B, heads=Hh, N=N, ms=round(ms, 4), tflops=round(4 * B * Hh * N * N * 64 / ms / 1e9, 1))), flush=True)
-    print(json.dumps(dict(kind='attention_diff', max_abs_1_vs_2=float((res[1] - res[2]).abs().max()), max_abs_1_vs_72=float((res[1] - res[72]).abs().max()))), flush=True)
+    print(json.dumps(dict(kind='attention_diff', max_abs_1_vs_2=float((res[1] - res[2]).abs().max()))), flush=True)
 lib.d3r_set_attention_impl(2)
