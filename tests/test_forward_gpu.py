@@ -46,7 +46,9 @@ def test_attention_matches_torch(cuda_device, impl):
     lib = _lib.get_lib()
     lib.d3r_set_attention_impl(impl)
     g = torch.Generator().manual_seed(0)
-    for (B, Hh, Nq, Nk) in [(2, 3, 24, 24), (1, 2, 196, 196), (2, 4, 768, 768), (1, 2, 100, 37), (3, 1, 65, 130)]:
+    # the last two shapes give the persistent kernel (impl 2) several tiles per CTA, one of them with ragged key blocks
+    for (B, Hh, Nq, Nk) in [(2, 3, 24, 24), (1, 2, 196, 196), (2, 4, 768, 768), (1, 2, 100, 37), (3, 1, 65, 130),
+                            (6, 16, 768, 768), (40, 8, 100, 137)]:
         q = torch.randn((B, Nq, Hh, 64), generator=g).to(cuda_device).bfloat16()
         k = torch.randn((B, Nk, Hh, 64), generator=g).to(cuda_device).bfloat16()
         v = torch.randn((B, Nk, Hh, 64), generator=g).to(cuda_device).bfloat16()

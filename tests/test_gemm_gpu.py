@@ -94,6 +94,33 @@ def test_gemm_epilogues(cuda_device):
 
 
 @pytest.mark.timeout(300)
+@pytest.mark.parametrize('M,N,K', [(777, 512, 320), (1000, 768, 1024), (130, 256, 64), (4100, 1024, 4096)])
+def test_gemm_specialised_epilogues(cuda_device, M, N, K):
+    """The compile-time epilogue specialisations (N % 256 == 0): residual update through TMA reduce-add (rows past M
+    are clipped by the tensor map), bias/GELU -> bf16, bias/ReLU -> bf16, with and without bias."""
+    A = _rand((M, K), cuda_device, seed=21).bfloat16()
+    B = _rand((N, K), cuda_device, scale=K ** -0.5, seed=22).bfloat16()
+    bias = _rand((N,), cuda_device, seed=23)
+    prod = A.float() @ B.float().T
+    tol = 3e-4 * max(1.0, (K / 320) ** 0.5)
+    # EPI_RESID: twice onto the same stream (the second update sees the first)
+    resid = _rand((M, N), cuda_device, seed=24)
+    guard = torch.full((8, N), 7.0, device=cuda_device)            # rows right behind the matrix must stay untouched
+    buf = torch.cat((resid, guard))
+    gemm(A, B, bias, F_BIAS | F_RESID_INPLACE, out=buf[:M])
+    assert (buf[:M] - (resid + prod + bias)).abs().max().item() < tol
+    gemm(A, B, None, F_RESID_INPLACE, out=buf[:M])
+    assert (buf[:M] - (resid + 2 * prod + bias)).abs().max().item() < 2 * tol
+    assert torch.equal(buf[M:], guard)
+    # EPI_ACT
+    out = gemm(A, B, bias, F_BIAS | F_GELU)
+    ref = torch.nn.functional.gelu(prod + bias)
+    assert (out.float() - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
+    out = gemm(A, B, None, F_RELU)
+    assert (out.float() - prod.relu()).abs().max().item() <= 2e-2 * max(1.0, prod.abs().max().item())
+
+
+@pytest.mark.timeout(300)
 def test_gemm_rope_matches_oracle(cuda_device):
     """QKV projection with fused 2D RoPE == oracle rope2d(linear) (croco/models/pos_embed.py:113-157)."""
     from oracle.forward_oracle import rope2d, positions, rope_tables
