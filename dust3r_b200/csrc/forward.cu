@@ -130,9 +130,12 @@ static int run_encoder(const Ctx& c, Arena& ar, const float* imgs, int n_enc, in
 struct DecBufs {
   __nv_bfloat16 *ln, *qkv, *att, *q, *kv, *hid;
 };
-static int dec_block(const Ctx& c, const d3r_dec_block& b, float* x, const __nv_bfloat16* ynorm, const DecBufs& w, int B) {
+static int dec_block(const Ctx& c, const Ctx& cy, const d3r_dec_block& b, float* x, const __nv_bfloat16* ynorm, const DecBufs& w,
+                     int B) {
+  // c: token grid of this branch (queries), cy: token grid of the other view (memory) -- they differ for pairs whose
+  // two images have different sizes (model.py:147-151 encodes such images separately)
   const d3r_model& m = *c.m;
-  const int D = m.dec_dim, M = B * c.N, hid = D * m.mlp_ratio;
+  const int D = m.dec_dim, M = B * c.N, My = B * cy.N, hid = D * m.mlp_ratio;
   const float scale = 1.0f / sqrtf(float(D / m.dec_heads));
   RC(ew::layernorm(x, b.norm1.g, b.norm1.b, w.ln, nullptr, M, D, m.ln_eps, c.st));
   RC(linear(c, w.ln, D, b.qkv, M, 3 * D, D, w.qkv, gemm::F_ROPE, nullptr, nullptr, 2 * D));
@@ -140,8 +143,8 @@ static int dec_block(const Ctx& c, const d3r_dec_block& b, float* x, const __nv_
   RC(linear(c, w.att, D, b.proj, M, D, D, x, gemm::F_RESID_INPLACE));
   RC(ew::layernorm(x, b.norm2.g, b.norm2.b, w.ln, nullptr, M, D, m.ln_eps, c.st));
   RC(linear(c, w.ln, D, b.projq, M, D, D, w.q, gemm::F_ROPE, nullptr, nullptr, D));
-  RC(linear(c, ynorm, D, b.projkv, M, 2 * D, D, w.kv, gemm::F_ROPE, nullptr, nullptr, D));  // k rotated, v not
-  RC(attn::attention_hd64(w.q, D, w.kv, 2 * D, w.kv + D, 2 * D, w.att, D, B, m.dec_heads, c.N, c.N, scale, c.st));
+  RC(linear(cy, ynorm, D, b.projkv, My, 2 * D, D, w.kv, gemm::F_ROPE, nullptr, nullptr, D));  // k rotated (memory positions), v not
+  RC(attn::attention_hd64(w.q, D, w.kv, 2 * D, w.kv + D, 2 * D, w.att, D, B, m.dec_heads, c.N, cy.N, scale, c.st));
   RC(linear(c, w.att, D, b.cproj, M, D, D, x, gemm::F_RESID_INPLACE));
   RC(ew::layernorm(x, b.norm3.g, b.norm3.b, w.ln, nullptr, M, D, m.ln_eps, c.st));
   RC(linear(c, w.ln, D, b.fc1, M, hid, D, w.hid, gemm::F_GELU));
@@ -245,48 +248,49 @@ static int run_dpt(const Ctx& c, Arena& ar, const d3r_dpt_head& hd, const void* 
   return D3R_OK;
 }
 
-static int forward(const d3r_model* mp, const float* imgs, int n_enc, const int32_t* idx1, const int32_t* idx2, int B, int H, int W,
-                   float* pts1, float* conf1, float* pts2, float* conf2, Arena& ar, cudaStream_t st) {
+// decoder + heads.  cv[br]: token grid of view br; enc[br]: encoder output holding view br's images; maps_host[br]: image
+// index of each pair inside enc[br] (nullptr = identity, pair b uses image b).
+static int decode_heads(const d3r_model* mp, const Ctx cv[2], const void* const enc[2], const int32_t* const maps_host[2], int B,
+                        float* pts1, float* conf1, float* pts2, float* conf2, Arena& ar, cudaStream_t st) {
   const d3r_model& m = *mp;
-  Ctx c{mp, st, H / m.patch, W / m.patch, (H / m.patch) * (W / m.patch)};
-  const int E = m.enc_dim, D = m.dec_dim, Md = B * c.N, hid = D * m.mlp_ratio;
+  const int E = m.enc_dim, D = m.dec_dim, hid = D * m.mlp_ratio;
+  const int Md[2] = {B * cv[0].N, B * cv[1].N};
+  const int Mx = Md[0] > Md[1] ? Md[0] : Md[1];
   typedef __nv_bfloat16 bf;
 
-  void* enc_out = nullptr;
-  const size_t mark_enc = ar.off;
-  RC(run_encoder(c, ar, imgs, n_enc, H, W, &enc_out));
-  // everything the encoder allocated except enc_out (its last allocation) can be reused: rewind to enc_out's end
-  (void)mark_enc;
-
-  // per-pair gathered encoder features (bf16): f1 = enc_out[idx1], f2 = enc_out[idx2]
+  // per-pair encoder features (bf16): f[br] = enc[br][maps[br]]
   bf* f[2];
-  f[0] = ar.arr<bf>((size_t)Md * E);
-  f[1] = ar.arr<bf>((size_t)Md * E);
+  f[0] = ar.arr<bf>((size_t)Md[0] * E);
+  f[1] = ar.arr<bf>((size_t)Md[1] * E);
   int* maps = ar.arr<int>((size_t)2 * B);
-  float* x[2] = {ar.arr<float>((size_t)Md * D), ar.arr<float>((size_t)Md * D)};
-  bf* yn[2] = {ar.arr<bf>((size_t)Md * D), ar.arr<bf>((size_t)Md * D)};
+  float* x[2] = {ar.arr<float>((size_t)Md[0] * D), ar.arr<float>((size_t)Md[1] * D)};
+  bf* yn[2] = {ar.arr<bf>((size_t)Md[1] * D), ar.arr<bf>((size_t)Md[0] * D)};   // yn[br]: the OTHER view, normalised for branch br
   DecBufs w;
-  w.ln = ar.arr<bf>((size_t)Md * D);
-  w.qkv = ar.arr<bf>((size_t)Md * 3 * D);
-  w.att = ar.arr<bf>((size_t)Md * D);
-  w.q = ar.arr<bf>((size_t)Md * D);
-  w.kv = ar.arr<bf>((size_t)Md * 2 * D);
-  w.hid = ar.arr<bf>((size_t)Md * hid);
+  w.ln = ar.arr<bf>((size_t)Mx * D);
+  w.qkv = ar.arr<bf>((size_t)Mx * 3 * D);
+  w.att = ar.arr<bf>((size_t)Mx * D);
+  w.q = ar.arr<bf>((size_t)Mx * D);
+  w.kv = ar.arr<bf>((size_t)Mx * 2 * D);
+  w.hid = ar.arr<bf>((size_t)Mx * hid);
   // hooked decoder outputs (bf16): hooks[1], hooks[2] raw; hooks[3] (= last) after dec_norm
   bf* hook[2][3];
   for (int br = 0; br < 2; ++br)
-    for (int k = 0; k < 3; ++k) hook[br][k] = ar.arr<bf>((size_t)Md * D);
+    for (int k = 0; k < 3; ++k) hook[br][k] = ar.arr<bf>((size_t)Md[br] * D);
   float* lin_feat = nullptr;
-  if (m.head_type == 0) lin_feat = ar.arr<float>((size_t)Md * m.nch * m.patch * m.patch);
+  if (m.head_type == 0) lin_feat = ar.arr<float>((size_t)Mx * m.nch * m.patch * m.patch);
 
   const size_t mark_head = ar.off;
   if (m.head_type == 1) {
-    // both heads reuse the same scratch region
-    Arena probe = ar;
-    const void* none[4] = {nullptr, nullptr, nullptr, nullptr};
-    probe.dry = true;
-    RC(run_dpt(c, probe, *m.dpt[0], none, B, nullptr, nullptr));
-    if (ar.dry) ar.off = probe.off;
+    // both heads reuse the same scratch region (sized for the larger view)
+    size_t top = ar.off;
+    for (int br = 0; br < 2; ++br) {
+      Arena probe = ar;
+      const void* none[4] = {nullptr, nullptr, nullptr, nullptr};
+      probe.dry = true;
+      RC(run_dpt(cv[br], probe, *m.dpt[br], none, B, nullptr, nullptr));
+      if (probe.off > top) top = probe.off;
+    }
+    if (ar.dry) ar.off = top;
   }
   if (ar.dry) return D3R_OK;
 
@@ -295,49 +299,52 @@ static int forward(const d3r_model* mp, const float* imgs, int n_enc, const int3
     return D3R_ERR_INVALID;
   }
 
-  D3R_CUDA(cudaMemcpyAsync(maps, idx1, sizeof(int) * B, cudaMemcpyHostToDevice, st));
-  D3R_CUDA(cudaMemcpyAsync(maps + B, idx2, sizeof(int) * B, cudaMemcpyHostToDevice, st));
-  RC(ew::gather_images_bf16(enc_out, f[0], maps, B, c.N, E, st));
-  RC(ew::gather_images_bf16(enc_out, f[1], maps + B, B, c.N, E, st));
+  for (int br = 0; br < 2; ++br) {
+    if (maps_host[br]) {
+      D3R_CUDA(cudaMemcpyAsync(maps + br * B, maps_host[br], sizeof(int) * B, cudaMemcpyHostToDevice, st));
+      RC(ew::gather_images_bf16(enc[br], f[br], maps + br * B, B, cv[br].N, E, st));
+    } else {
+      D3R_CUDA(cudaMemcpyAsync(f[br], enc[br], sizeof(bf) * (size_t)Md[br] * E, cudaMemcpyDeviceToDevice, st));
+    }
+  }
 
   // decoder (model.py:172-191)
-  RC(linear(c, f[0], E, m.decoder_embed, Md, D, E, x[0], gemm::F_OUT_F32));
-  RC(linear(c, f[1], E, m.decoder_embed, Md, D, E, x[1], gemm::F_OUT_F32));
-  tap_f32(5, x[0], (size_t)Md * D, st);
+  RC(linear(cv[0], f[0], E, m.decoder_embed, Md[0], D, E, x[0], gemm::F_OUT_F32));
+  RC(linear(cv[1], f[1], E, m.decoder_embed, Md[1], D, E, x[1], gemm::F_OUT_F32));
+  tap_f32(5, x[0], (size_t)Md[0] * D, st);
   for (int l = 0; l < m.dec_depth; ++l) {
     // memory normalisation of the *previous* outputs, each with the consuming block's norm_y
-    RC(ew::layernorm(x[1], m.dec1[l].norm_y.g, m.dec1[l].norm_y.b, yn[0], nullptr, Md, D, m.ln_eps, st));  // for branch 1
-    RC(ew::layernorm(x[0], m.dec2[l].norm_y.g, m.dec2[l].norm_y.b, yn[1], nullptr, Md, D, m.ln_eps, st));  // for branch 2
-    RC(dec_block(c, m.dec1[l], x[0], yn[0], w, B));
-    RC(dec_block(c, m.dec2[l], x[1], yn[1], w, B));
-    if (l == 0) { tap_f32(6, x[0], (size_t)Md * D, st); tap_f32(7, x[1], (size_t)Md * D, st); }
+    RC(ew::layernorm(x[1], m.dec1[l].norm_y.g, m.dec1[l].norm_y.b, yn[0], nullptr, Md[1], D, m.ln_eps, st));  // for branch 1
+    RC(ew::layernorm(x[0], m.dec2[l].norm_y.g, m.dec2[l].norm_y.b, yn[1], nullptr, Md[0], D, m.ln_eps, st));  // for branch 2
+    RC(dec_block(cv[0], cv[1], m.dec1[l], x[0], yn[0], w, B));
+    RC(dec_block(cv[1], cv[0], m.dec2[l], x[1], yn[1], w, B));
+    if (l == 0) { tap_f32(6, x[0], (size_t)Md[0] * D, st); tap_f32(7, x[1], (size_t)Md[1] * D, st); }
     for (int k = 1; k <= 2; ++k) {
       if (m.head_type == 1 && l + 1 == m.hooks[k]) {
-        RC(ew::cast_f32_bf16(x[0], hook[0][k - 1], (size_t)Md * D, st));
-        RC(ew::cast_f32_bf16(x[1], hook[1][k - 1], (size_t)Md * D, st));
+        RC(ew::cast_f32_bf16(x[0], hook[0][k - 1], (size_t)Md[0] * D, st));
+        RC(ew::cast_f32_bf16(x[1], hook[1][k - 1], (size_t)Md[1] * D, st));
       }
     }
   }
-  tap_f32(8, x[0], (size_t)Md * D, st);
-  tap_f32(9, x[1], (size_t)Md * D, st);
-  RC(ew::layernorm(x[0], m.dec_norm.g, m.dec_norm.b, hook[0][2], nullptr, Md, D, m.ln_eps, st));
-  RC(ew::layernorm(x[1], m.dec_norm.g, m.dec_norm.b, hook[1][2], nullptr, Md, D, m.ln_eps, st));
+  tap_f32(8, x[0], (size_t)Md[0] * D, st);
+  tap_f32(9, x[1], (size_t)Md[1] * D, st);
+  RC(ew::layernorm(x[0], m.dec_norm.g, m.dec_norm.b, hook[0][2], nullptr, Md[0], D, m.ln_eps, st));
+  RC(ew::layernorm(x[1], m.dec_norm.g, m.dec_norm.b, hook[1][2], nullptr, Md[1], D, m.ln_eps, st));
 
+  float* outs[2][2] = {{pts1, conf1}, {pts2, conf2}};
   if (m.head_type == 0) {
     const int nf = m.nch * m.patch * m.patch;
-    float* outs[2][2] = {{pts1, conf1}, {pts2, conf2}};
     for (int br = 0; br < 2; ++br) {
-      RC(linear(c, hook[br][2], D, m.lin_head[br], Md, nf, D, lin_feat, gemm::F_OUT_F32));
-      RC(ew::linear_head_postprocess(lin_feat, outs[br][0], outs[br][1], B, c.gh, c.gw, m.nch, m.depth_mode, m.conf_mode,
+      RC(linear(cv[br], hook[br][2], D, m.lin_head[br], Md[br], nf, D, lin_feat, gemm::F_OUT_F32));
+      RC(ew::linear_head_postprocess(lin_feat, outs[br][0], outs[br][1], B, cv[br].gh, cv[br].gw, m.nch, m.depth_mode, m.conf_mode,
                                      m.conf_min, m.conf_max, st));
     }
   } else {
-    float* outs[2][2] = {{pts1, conf1}, {pts2, conf2}};
     for (int br = 0; br < 2; ++br) {
       Arena head = ar;
       head.off = mark_head;
       const void* tok[4] = {f[br], hook[br][0], hook[br][1], hook[br][2]};
-      RC(run_dpt(c, head, *m.dpt[br], tok, B, outs[br][0], outs[br][1]));
+      RC(run_dpt(cv[br], head, *m.dpt[br], tok, B, outs[br][0], outs[br][1]));
       if (head.off > head.cap) {
         set_error("forward: workspace too small (%zu > %zu bytes)", head.off, head.cap);
         return D3R_ERR_INVALID;
@@ -345,6 +352,37 @@ static int forward(const d3r_model* mp, const float* imgs, int n_enc, const int3
     }
   }
   return D3R_OK;
+}
+
+// all images share one size: one encoder pass over the n_enc distinct images, pairs address them through idx1 / idx2
+static int forward(const d3r_model* mp, const float* imgs, int n_enc, const int32_t* idx1, const int32_t* idx2, int B, int H, int W,
+                   float* pts1, float* conf1, float* pts2, float* conf2, Arena& ar, cudaStream_t st) {
+  const d3r_model& m = *mp;
+  Ctx c{mp, st, H / m.patch, W / m.patch, (H / m.patch) * (W / m.patch)};
+  void* enc_out = nullptr;
+  RC(run_encoder(c, ar, imgs, n_enc, H, W, &enc_out));
+  const Ctx cv[2] = {c, c};
+  const void* enc[2] = {enc_out, enc_out};
+  const int32_t* maps[2] = {idx1, idx2};
+  // a dry (size-only) pass has no index lists; the gather path is what the real call takes
+  static const int32_t kDummy = 0;
+  if (ar.dry) maps[0] = maps[1] = &kDummy;
+  return decode_heads(mp, cv, enc, maps, B, pts1, conf1, pts2, conf2, ar, st);
+}
+
+// the two views of every pair have different sizes (all first views H1 x W1, all second views H2 x W2): the reference
+// encodes them separately (model.py:147-151) and the decoder cross-attends between the two token grids
+static int forward_mixed(const d3r_model* mp, const float* imgs1, int H1, int W1, const float* imgs2, int H2, int W2, int B, float* pts1,
+                         float* conf1, float* pts2, float* conf2, Arena& ar, cudaStream_t st) {
+  const d3r_model& m = *mp;
+  const Ctx cv[2] = {Ctx{mp, st, H1 / m.patch, W1 / m.patch, (H1 / m.patch) * (W1 / m.patch)},
+                     Ctx{mp, st, H2 / m.patch, W2 / m.patch, (H2 / m.patch) * (W2 / m.patch)}};
+  void* e[2] = {nullptr, nullptr};
+  RC(run_encoder(cv[0], ar, imgs1, B, H1, W1, &e[0]));
+  RC(run_encoder(cv[1], ar, imgs2, B, H2, W2, &e[1]));
+  const void* enc[2] = {e[0], e[1]};
+  const int32_t* maps[2] = {nullptr, nullptr};
+  return decode_heads(mp, cv, enc, maps, B, pts1, conf1, pts2, conf2, ar, st);
 }
 
 }  // namespace fwd
@@ -384,6 +422,29 @@ extern "C" int d3r_forward_pairs(const d3r_model* m, const float* imgs_dev, int3
   D3R_CHECK_ARG(need > 0 && workspace_bytes >= need, "forward: workspace of %lld bytes needed, %lld given", (long long)need, (long long)workspace_bytes);
   fwd::Arena ar{reinterpret_cast<uint8_t*>(workspace_dev), (size_t)workspace_bytes, 0, false};
   rc = fwd::forward(m, imgs_dev, n_enc, idx1_host, idx2_host, B, H, W, pts3d_1, conf_1, pts3d_2, conf_2, ar, (cudaStream_t)stream);
+  fwd::g_tap = {-1, nullptr, 0};
+  return rc;
+}
+
+extern "C" int64_t d3r_forward_mixed_workspace_bytes(const d3r_model* m, int32_t B, int32_t H1, int32_t W1, int32_t H2, int32_t W2) {
+  if (check_model(m, H1, W1) || check_model(m, H2, W2)) return -1;
+  fwd::Arena ar{nullptr, 0, 0, true};
+  if (fwd::forward_mixed(m, nullptr, H1, W1, nullptr, H2, W2, B, nullptr, nullptr, nullptr, nullptr, ar, 0)) return -1;
+  return (int64_t)ar.off + 4096;
+}
+
+extern "C" int d3r_forward_pairs_mixed(const d3r_model* m, const float* imgs1_dev, int32_t H1, int32_t W1, const float* imgs2_dev,
+                                       int32_t H2, int32_t W2, int32_t B, float* pts3d_1, float* conf_1, float* pts3d_2,
+                                       float* conf_2, void* workspace_dev, int64_t workspace_bytes, void* stream) {
+  int rc = check_model(m, H1, W1);
+  if (rc) return rc;
+  if ((rc = check_model(m, H2, W2))) return rc;
+  D3R_CHECK_ARG(imgs1_dev && imgs2_dev && pts3d_1 && pts3d_2 && workspace_dev, "forward: null buffer");
+  D3R_CHECK_ARG(B > 0, "forward: empty batch");
+  const int64_t need = d3r_forward_mixed_workspace_bytes(m, B, H1, W1, H2, W2);
+  D3R_CHECK_ARG(need > 0 && workspace_bytes >= need, "forward: workspace of %lld bytes needed, %lld given", (long long)need, (long long)workspace_bytes);
+  fwd::Arena ar{reinterpret_cast<uint8_t*>(workspace_dev), (size_t)workspace_bytes, 0, false};
+  rc = fwd::forward_mixed(m, imgs1_dev, H1, W1, imgs2_dev, H2, W2, B, pts3d_1, conf_1, pts3d_2, conf_2, ar, (cudaStream_t)stream);
   fwd::g_tap = {-1, nullptr, 0};
   return rc;
 }

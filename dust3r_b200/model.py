@@ -189,8 +189,6 @@ class AsymmetricCroCo3DStereo(nn.Module, _HubMixin, **_hub_kwargs):
     def forward(self, view1, view2):
         img1, img2 = view1['img'], view2['img']
         B = img1.shape[0]
-        if img1.shape[-2:] != img2.shape[-2:]:
-            raise NotImplementedError('pairs whose two images differ in size are not supported by the fused path yet')
         dev = img1.device
         _lib.require_cuda_device(dev)
         if self._packed is None or self._packed.device != dev:
@@ -198,16 +196,22 @@ class AsymmetricCroCo3DStereo(nn.Module, _HubMixin, **_hub_kwargs):
                 raise _lib.D3RError(f'model parameters live on {next(self.parameters()).device}, images on {dev}')
             self.repack()
         H, W = int(img1.shape[-2]), int(img1.shape[-1])
+        H2, W2 = int(img2.shape[-2]), int(img2.shape[-1])
         shape1 = view1.get('true_shape', torch.tensor(img1.shape[-2:])[None].repeat(B, 1))
         shape2 = view2.get('true_shape', torch.tensor(img2.shape[-2:])[None].repeat(B, 1))
-        for ts in (shape1, shape2):
+        for ts, (Hv, Wv) in ((shape1, (H, W)), (shape2, (H2, W2))):
             ts = torch.as_tensor(ts)
             assert ts[0:1].allclose(ts), 'true_shape must be all identical'
             h, w = [int(v) for v in ts[0].tolist()]
-            if (h, w) != (H, W):
-                if self.landscape_only and (w, h) == (H, W):
+            if (h, w) != (Hv, Wv):
+                if self.landscape_only and (w, h) == (Hv, Wv):
                     raise NotImplementedError('portrait images under landscape_only=True (training-time ManyAR path)')
-                raise AssertionError(f'true_shape {(h, w)} does not match the image tensor {(H, W)}')
+                raise AssertionError(f'true_shape {(h, w)} does not match the image tensor {(Hv, Wv)}')
+        if (H, W) != (H2, W2):
+            # model.py:147-151: the two views are encoded separately; the decoder cross-attends between the two grids
+            res1, res2 = self._packed.forward_mixed(img1.float().contiguous(), img2.float().contiguous())
+            res2['pts3d_in_other_view'] = res2.pop('pts3d')
+            return res1, res2
         # model.py:153-170: a batch [(a,b),(b,a),...] only encodes its even half
         if is_symmetrized(view1, view2):
             imgs = torch.cat((img1[::2], img2[::2]), dim=0)
@@ -365,6 +369,35 @@ class _PackedModel:
             self._ws = torch.empty((need,), dtype=torch.uint8, device=self.device)
             self._ws_key = key
         return self._ws
+
+    def forward_mixed(self, imgs1, imgs2):
+        """imgs1 (B,3,H1,W1), imgs2 (B,3,H2,W2) fp32 CUDA with different sizes -> ({'pts3d','conf'}, {'pts3d','conf'})."""
+        B = int(imgs1.shape[0])
+        assert int(imgs2.shape[0]) == B
+        H1, W1, H2, W2 = int(imgs1.shape[-2]), int(imgs1.shape[-1]), int(imgs2.shape[-2]), int(imgs2.shape[-1])
+        key = ('mixed', B, H1, W1, H2, W2)
+        if self._ws_key != key:
+            need = self.lib.d3r_forward_mixed_workspace_bytes(C.byref(self.cmodel), B, H1, W1, H2, W2)
+            if need <= 0:
+                _lib.check(-1)
+            self._ws = None
+            self._ws = torch.empty((need,), dtype=torch.uint8, device=self.device)
+            self._ws_key = key
+        dev = self.device
+        has_conf = self.cmodel.nch > 3
+        pts1 = torch.empty((B, H1, W1, 3), dtype=torch.float32, device=dev)
+        pts2 = torch.empty((B, H2, W2, 3), dtype=torch.float32, device=dev)
+        conf1 = torch.empty((B, H1, W1), dtype=torch.float32, device=dev) if has_conf else None
+        conf2 = torch.empty((B, H2, W2), dtype=torch.float32, device=dev) if has_conf else None
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.d3r_forward_pairs_mixed(C.byref(self.cmodel), imgs1.data_ptr(), H1, W1, imgs2.data_ptr(), H2, W2, B,
+                                                        pts1.data_ptr(), conf1.data_ptr() if has_conf else None,
+                                                        pts2.data_ptr(), conf2.data_ptr() if has_conf else None,
+                                                        self._ws.data_ptr(), self._ws.numel(), _lib.stream_ptr()))
+        r1, r2 = {'pts3d': pts1}, {'pts3d': pts2}
+        if has_conf:
+            r1['conf'], r2['conf'] = conf1, conf2
+        return r1, r2
 
     def forward(self, imgs, idx1, idx2, B, H, W, debug=None):
         """imgs: (n_enc,3,H,W) fp32 CUDA.  Returns ({'pts3d','conf'}, {'pts3d','conf'}) CUDA fp32 tensors."""

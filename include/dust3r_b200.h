@@ -270,6 +270,15 @@ int d3r_forward_pairs(const d3r_model* m, const float* imgs_dev, int32_t n_enc, 
                       const int32_t* idx2_host, int32_t B, int32_t H, int32_t W, float* pts3d_1, float* conf_1,
                       float* pts3d_2, float* conf_2, void* workspace_dev, int64_t workspace_bytes, void* stream);
 
+/* Pairs whose two images differ in size (the reference encodes them separately, dust3r/model.py:147-151, and
+ * inference() then runs one pair per call, dust3r/inference.py:60-64): imgs1 (B,3,H1,W1) are the first views,
+ * imgs2 (B,3,H2,W2) the second views; outputs pts3d_1 (B,H1,W1,3), conf_1 (B,H1,W1), pts3d_2 (B,H2,W2,3),
+ * conf_2 (B,H2,W2).  No symmetrisation shortcut on this path. */
+int64_t d3r_forward_mixed_workspace_bytes(const d3r_model* m, int32_t B, int32_t H1, int32_t W1, int32_t H2, int32_t W2);
+int d3r_forward_pairs_mixed(const d3r_model* m, const float* imgs1_dev, int32_t H1, int32_t W1, const float* imgs2_dev,
+                            int32_t H2, int32_t W2, int32_t B, float* pts3d_1, float* conf_1, float* pts3d_2,
+                            float* conf_2, void* workspace_dev, int64_t workspace_bytes, void* stream);
+
 /* Optional taps for the parity tests: when non-NULL, fp32 copies of intermediate stages are written.
  * (set with d3r_forward_set_debug before a call; cleared after it).  stage ids in DESIGN.md. */
 int d3r_forward_set_debug(int32_t stage_id, float* out_dev, int64_t capacity_floats);

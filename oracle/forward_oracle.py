@@ -262,8 +262,7 @@ def is_symmetrized(inst1, inst2):
 @torch.no_grad()
 def forward_oracle(sd, cfg, img1, img2, instance1=None, instance2=None, stages=None):
     """Full pair forward.  Returns (res1, res2) like AsymmetricCroCo3DStereo.forward (model.py:199-211).
-    Same-size images only (the benchmarked case); different sizes encode separately in the reference
-    and the maths is identical."""
+    Pairs whose two images differ in size are encoded separately (model.py:147-151)."""
     sd = {k: v.float() for k, v in sd.items()}
     B = img1.shape[0]
     sym = instance1 is not None and is_symmetrized(instance1, instance2)
@@ -275,6 +274,10 @@ def forward_oracle(sd, cfg, img1, img2, instance1=None, instance2=None, stages=N
         f2 = torch.stack((b, a), 1).flatten(0, 1)
         pos1 = torch.stack((pa, pb), 1).flatten(0, 1)
         pos2 = torch.stack((pb, pa), 1).flatten(0, 1)
+    elif img1.shape[-2:] != img2.shape[-2:]:
+        # model.py:147-151 (_encode_image_pairs): images of different sizes are encoded separately
+        f1, pos1 = encode(img1, sd, cfg, stages)
+        f2, pos2 = encode(img2, sd, cfg, None)
     else:
         e, pos = encode(torch.cat((img1, img2)), sd, cfg, stages)
         f1, f2 = e.chunk(2)

@@ -80,6 +80,30 @@ def forward_goldens():
         print('wrote', name)
 
 
+def forward_mixed_goldens():
+    from dust3r.inference import inference
+    from dust3r.image_pairs import make_pairs
+    # mixed image sizes: three images of different sizes, all 6 ordered pairs -> the reference forces batch size 1,
+    # returns lists, and encodes the two views of every pair separately (model.py:147-151)
+    for name, (cfg, H, W) in SMALL.items():
+        torch.manual_seed(0)
+        m = ref_model(cfg)
+        sd = synth_state_dict(cfg, seed=11)
+        m.load_state_dict(sd, strict=True)
+        sizes = [(H, W), (H - 16, W), (H, W - 32)]
+        imgs = [dict(synth_images(1, h, w, seed=20 + k)[0], idx=k, instance=str(k)) for k, (h, w) in enumerate(sizes)]
+        pairs = make_pairs(imgs, scene_graph='complete', prefilter=None, symmetrize=True)
+        out = inference(pairs, m, 'cpu', batch_size=4, verbose=False)
+        res = dict(idx1=np.int64(out['view1']['idx']), idx2=np.int64(out['view2']['idx']))
+        for k in range(len(pairs)):
+            res[f'pts3d_{k}'] = out['pred1']['pts3d'][k].numpy()
+            res[f'conf1_{k}'] = out['pred1']['conf'][k].numpy()
+            res[f'pts3d_in_other_view_{k}'] = out['pred2']['pts3d_in_other_view'][k].numpy()
+            res[f'conf2_{k}'] = out['pred2']['conf'][k].numpy()
+        np.savez_compressed(os.path.join(HERE, f'forward_{name}_mixed.npz'), **res)
+        print('wrote mixed', name, [tuple(out['pred1']['pts3d'][k].shape) for k in range(len(pairs))])
+
+
 def pair_goldens():
     from dust3r.image_pairs import make_pairs
     res = {}
@@ -149,3 +173,5 @@ if __name__ == '__main__':
     with torch.no_grad():
         if 'forward' in what:
             forward_goldens()
+        if 'forward' in what or 'mixed' in what:
+            forward_mixed_goldens()

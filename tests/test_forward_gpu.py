@@ -89,6 +89,30 @@ def test_forward_matches_oracle_and_reference_golden(cuda_device, name):
 
 
 @pytest.mark.timeout(900)
+@pytest.mark.parametrize('name', ['small_dpt', 'small_linear'])
+def test_forward_mixed_sizes_matches_reference_golden(cuda_device, name):
+    """Three images of three sizes, all ordered pairs: inference() returns lists (inference.py:60-72) and every pair
+    runs through d3r_forward_pairs_mixed (separate encoder passes, cross-attention between two token grids)."""
+    from dust3r_b200.inference import inference
+    cfg, H, W = _small_cfgs()[name]
+    net, sd = _build(cfg, 11, cuda_device)
+    sizes = [(H, W), (H - 16, W), (H, W - 32)]
+    imgs = [dict(synth_images(1, h, w, seed=20 + k)[0], idx=k, instance=str(k)) for k, (h, w) in enumerate(sizes)]
+    pairs = make_pairs(imgs, scene_graph='complete', prefilter=None, symmetrize=True)
+    out = inference(pairs, net, cuda_device, batch_size=4, verbose=False)
+    gold = np.load(os.path.join(GOLDEN, f'forward_{name}_mixed.npz'))
+    assert out['view1']['idx'] == gold['idx1'].tolist() and out['view2']['idx'] == gold['idx2'].tolist()
+    assert isinstance(out['pred1']['pts3d'], list) and len(out['pred1']['pts3d']) == len(pairs)
+    for k in range(len(pairs)):
+        for got, key in ((out['pred1']['pts3d'][k], f'pts3d_{k}'), (out['pred1']['conf'][k], f'conf1_{k}'),
+                         (out['pred2']['pts3d_in_other_view'][k], f'pts3d_in_other_view_{k}'), (out['pred2']['conf'][k], f'conf2_{k}')):
+            ref = torch.from_numpy(gold[key])
+            got = got.reshape(ref.shape) if got.numel() == ref.numel() else got
+            assert got.shape == ref.shape and got.device.type == 'cpu' and torch.isfinite(got).all(), (key, got.shape, ref.shape)
+            assert _rel(got, ref) < 3e-2, (key, _rel(got, ref))
+
+
+@pytest.mark.timeout(900)
 def test_inference_pipelined_micro_batches_bit_identical(cuda_device):
     """batch_size >= 16 runs as two pipelined halves (upload / compute / download overlap): the result must be
     bit-identical to small unpipelined batches, in pair order, for symmetrised and plain pair lists."""

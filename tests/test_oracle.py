@@ -60,6 +60,30 @@ def test_forward_oracle_matches_reference_golden(name):
         assert torch.allclose(out[k], ref, rtol=2e-4, atol=2e-5), (k, float((out[k] - ref).abs().max()))
 
 
+def _mixed_size_pairs(H, W):
+    sizes = [(H, W), (H - 16, W), (H, W - 32)]
+    imgs = [dict(synth_images(1, h, w, seed=20 + k)[0], idx=k, instance=str(k)) for k, (h, w) in enumerate(sizes)]
+    return make_pairs(imgs, scene_graph='complete', prefilter=None, symmetrize=True)
+
+
+@pytest.mark.parametrize('name', ['small_dpt', 'small_linear'])
+def test_forward_oracle_mixed_sizes_matches_reference_golden(name):
+    """Pairs whose two images differ in size: the reference runs them one pair per call and encodes the two views
+    separately (inference.py:60-64, model.py:147-151); fixtures made by the unmodified reference."""
+    cfg, H, W = _small_cfgs()[name]
+    sd = synth_state_dict(cfg, seed=11)
+    pairs = _mixed_size_pairs(H, W)
+    gold = np.load(os.path.join(GOLDEN, f'forward_{name}_mixed.npz'))
+    assert [a['idx'] for a, b in pairs] == gold['idx1'].tolist() and [b['idx'] for a, b in pairs] == gold['idx2'].tolist()
+    for k, (a, b) in enumerate(pairs):
+        r1, r2 = forward_oracle(sd, cfg, a['img'], b['img'], [a['instance']], [b['instance']])
+        for got, key in ((r1['pts3d'][0], f'pts3d_{k}'), (r1['conf'][0], f'conf1_{k}'),
+                         (r2['pts3d_in_other_view'][0], f'pts3d_in_other_view_{k}'), (r2['conf'][0], f'conf2_{k}')):
+            ref = torch.from_numpy(gold[key])
+            assert got.shape == ref.shape
+            assert (got - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item()), (key, (got - ref).abs().max().item())
+
+
 def test_forward_oracle_matches_reference_golden_vitl_224_linear():
     from dust3r_b200.config import vitl_224_linear
     cfg = vitl_224_linear()
