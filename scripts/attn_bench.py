@@ -10,7 +10,7 @@ for (B, Hh, N) in [(64, 16, 768), (32, 12, 768)]:
     qkv = torch.randn((B, N, ld), device='cuda').bfloat16()
     out = torch.empty((B, N, Hh * 64), device='cuda', dtype=torch.bfloat16)
     res = {}
-    for impl in (1, 31, 41, 2):   # impl 1 with 3 / 2 / 1 CTAs per SM (shared-memory padding), impl 2
+    for impl in (1, 2, 12, 32):   # impl 1, impl 2, impl 2 without exp2 / without any softmax work (timing ablations)
         lib.d3r_set_attention_impl(impl)
         def f():
             _lib.check(lib.d3r_attention_hd64(qkv.data_ptr(), ld, qkv.data_ptr() + Hh * 128, ld, qkv.data_ptr() + Hh * 256, ld,
