@@ -487,7 +487,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       // accumulator drained: hand the TMEM buffer back to the MMA warp
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[acc]));
+      if (lane == 0) ptx::mbar_arrive_relaxed(ptx::smem_u32(&tempty_bar[acc]));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
 
       if ((flags & F_HEAD_FINAL) && valid && half == 0) {

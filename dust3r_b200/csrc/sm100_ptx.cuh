@@ -39,6 +39,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// arrival that publishes no memory (e.g. "my tcgen05.ld of this accumulator are complete"): no release fence
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
   asm volatile(
@@ -154,13 +158,17 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster.
+// RELAXED on purpose: the only thing this arrival publishes is "my tcgen05.ld of the accumulator have completed",
+// which tcgen05.wait::ld (+ tcgen05.fence::before_thread_sync) already guarantees in program order.  A
+// .release.cluster arrive compiles to MEMBAR.ALL.CTA + ERRBAR, which drains every outstanding global store / TMA
+// reduce of the warp first (24 % of the stall samples of the residual-update GEMM, profiles/r01_prof_kernels_v12).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
   asm volatile(
       "{\n"
       ".reg .b32 raddr;\n"
       "mapa.shared::cluster.u32 raddr, %0, %1;\n"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [raddr];\n"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [raddr];\n"
       "}\n" ::"r"(bar), "r"(rank) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
