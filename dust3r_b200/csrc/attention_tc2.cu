@@ -284,7 +284,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(s_free));
+        if (lane == 0) ptx::mbar_arrive_relaxed(ptx::smem_u32(s_free));   // publishes only completed TMEM loads
         float mx = -INFINITY;
 #pragma unroll
         for (int i = 0; i < 64; ++i)
@@ -316,7 +316,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         // S_j fully read (by this warp) -> after all eight arrivals the MMA warp may overwrite it with S_{j+1}
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(s_free));
+        if (lane == 0) ptx::mbar_arrive_relaxed(ptx::smem_u32(s_free));   // publishes only completed TMEM loads
         exp_chunk(rbuf[1], 1);
       }
       A2_STAMP(g, 2);
@@ -395,7 +395,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     // O is in registers: the MMA warp may start the next tile's P V
     ptx::tc_fence_before();
     __syncwarp();
-    if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(o_free));
+    if (lane == 0) ptx::mbar_arrive_relaxed(ptx::smem_u32(o_free));
     const int qrow = q0 + row;
     if (qrow < Nq) {
       uint4* o4 = reinterpret_cast<uint4*>(out + ((long long)b * Nq + qrow) * ldo + h * D + half * 32);
