@@ -489,6 +489,14 @@ align_iter_kernel(const __grid_constant__ d3r_align_desc D, int it) {
   if (tid == 0)
     for (int k = 0; k < min(kStages, deg); ++k) produce(k);
 
+  // Programmatic dependent launch: everything above touches only per-problem constants (index tables, the
+  // observation slabs) -- this iteration's CTAs were allowed to start it while the previous iteration's last CTA
+  // was still in its small-parameter step.  Everything below reads what that step (and the previous depth update)
+  // wrote, so wait here for the previous grid to complete and flush.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // ... and allow the NEXT iteration's CTAs to be scheduled as soon as every CTA of this grid has got this far: they
+  // take the slots of this grid's last wave as its CTAs retire, and block at their own griddepcontrol.wait
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const float* iT = ws.imgT + img * kImgT;
   float R[9], T[3];
 #pragma unroll
@@ -721,7 +729,17 @@ static int launch_iters(const d3r_align_desc* desc, int it_begin, int it_end, cu
     D3R_CUDA(cudaFuncSetAttribute(align_iter_kernel<kL2, PPT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr = true;
   }
-  for (int it = it_begin; it < it_end; ++it) align_iter_kernel<kL2, PPT><<<desc->n_chunks, kThreads, smem, st>>>(*desc, it);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)desc->n_chunks);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // overlap a launch's prologue with its predecessor's tail
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  for (int it = it_begin; it < it_end; ++it) D3R_CUDA(cudaLaunchKernelEx(&cfg, align_iter_kernel<kL2, PPT>, *desc, it));
   D3R_LAUNCH_CHECK();
   return D3R_OK;
 }
