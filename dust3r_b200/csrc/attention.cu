@@ -9,6 +9,7 @@
 #include "d3r_common.cuh"
 #include "elementwise.h"
 #include "prof.h"
+#include "pdl.cuh"
 #include <cuda_bf16.h>
 
 namespace d3r {
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(kThreads) attention_kernel(const __nv_bfloat16
                                                              const __nv_bfloat16* __restrict__ v, long long ldv,
                                                              __nv_bfloat16* __restrict__ out, long long ldo, int Nq, int Nk,
                                                              float scale_log2) {
+  pdl::sync_with_predecessor();   // PDL: nothing above touches memory produced by other kernels
   __shared__ __align__(128) uint8_t s_q[BM * 128];
   __shared__ __align__(128) uint8_t s_k[2][BN * 128];
   __shared__ __align__(128) uint8_t s_v[2][BN * 128];
@@ -199,8 +201,8 @@ int attention_hd64(const void* q, long long ldq, const void* k, long long ldk, c
   D3R_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 2 == 0, "attention: row strides must keep 16-byte alignment");
   dim3 grid((Nq + BM - 1) / BM, heads, B);
   prof::Scope scope("attention_hd64", st, 4.0 * double(B) * heads * double(Nq) * double(Nk) * 64.0);
-  attention_kernel<<<grid, kThreads, 0, st>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk, (const __nv_bfloat16*)v, ldv,
-                                               (__nv_bfloat16*)out, ldo, Nq, Nk, scale * 1.4426950408889634f);
+  D3R_CUDA(pdl::launch(attention_kernel, grid, dim3(kThreads), 0, st, (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk,
+                       (const __nv_bfloat16*)v, ldv, (__nv_bfloat16*)out, ldo, Nq, Nk, scale * 1.4426950408889634f));
   D3R_LAUNCH_CHECK();
   return D3R_OK;
 }

@@ -18,6 +18,7 @@
 #include "elementwise.h"
 #include "prof.h"
 #include "attention_tc_common.cuh"
+#include "pdl.cuh"
 #include <type_traits>
 
 namespace d3r {
@@ -108,6 +109,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl::sync_with_predecessor();   // set-up done; from here on the kernel reads q/k/v written by its predecessor
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -375,8 +377,8 @@ int attention_hd64_tc(const void* q, long long ldq, const void* k, long long ldk
   }
   dim3 grid((Nq + tc::BQ - 1) / tc::BQ, heads, B);
   prof::Scope scope("attention_tcgen05", st, 4.0 * double(B) * heads * double(Nq) * double(Nk) * 64.0);
-  tc::attention_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes + g_occupancy_pad, st>>>(mq, mk, mv, (__nv_bfloat16*)out, ldo, Nq, Nk, 0, 0, 0,
-                                                                     scale * 1.4426950408889634f);
+  D3R_CUDA(pdl::launch(tc::attention_tc_kernel, grid, dim3(tc::kThreads), size_t(tc::kSmemBytes + g_occupancy_pad), st, mq, mk, mv,
+                       (__nv_bfloat16*)out, ldo, Nq, Nk, 0, 0, 0, scale * 1.4426950408889634f));
   D3R_LAUNCH_CHECK();
   return D3R_OK;
 }

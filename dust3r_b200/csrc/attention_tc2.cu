@@ -27,6 +27,7 @@
 #include "elementwise.h"
 #include "prof.h"
 #include "attention_tc_common.cuh"
+#include "pdl.cuh"
 #include <type_traits>
 
 namespace d3r {
@@ -148,6 +149,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl::sync_with_predecessor();   // set-up done; from here on the kernel reads q/k/v written by its predecessor
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -471,8 +473,8 @@ static int launch_tc2(const CUtensorMap& mq, const CUtensorMap& mk, const CUtens
   const int rounds = (total_tiles + slots - 1) / slots;
   const int grid = (total_tiles + rounds - 1) / rounds;
   prof::Scope scope("attention_tcgen05_split", st, 4.0 * double(B) * heads * double(Nq) * double(Nk) * 64.0);
-  tc2::attention_tc2_kernel<ABL, POLY><<<grid, tc2::kThreads, tc2::kSmemBytes, st>>>(mq, mk, mv, (__nv_bfloat16*)out, ldo, Nq, Nk, heads,
-                                                                              total_tiles, scale * 1.4426950408889634f);
+  D3R_CUDA(pdl::launch(tc2::attention_tc2_kernel<ABL, POLY>, dim3(grid), dim3(tc2::kThreads), size_t(tc2::kSmemBytes), st, mq, mk, mv,
+                       (__nv_bfloat16*)out, ldo, Nq, Nk, heads, total_tiles, scale * 1.4426950408889634f));
   D3R_LAUNCH_CHECK();
   return D3R_OK;
 }

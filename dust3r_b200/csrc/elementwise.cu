@@ -5,6 +5,7 @@
 #include "d3r_common.cuh"
 #include "elementwise.h"
 #include "prof.h"
+#include "pdl.cuh"
 #include <cuda_bf16.h>
 
 namespace d3r {
@@ -20,6 +21,7 @@ template <int MAXV>  // float4 per lane
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                         const float* __restrict__ b, __nv_bfloat16* __restrict__ out,
                                                         const int* __restrict__ row_map, int M, int C, float eps) {
+  pdl::sync_with_predecessor();   // PDL: nothing above touches memory produced by other kernels
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -71,15 +73,16 @@ int layernorm(const float* x, const float* g, const float* b, void* out_bf16, co
   const int blocks = (M + warps - 1) / warps;
   prof::Scope scope("layernorm", st, 0.0, double(M) * C * 6.0);
   if (C <= 1024)
-    layernorm_kernel<8><<<blocks, warps * 32, 0, st>>>(x, g, b, (__nv_bfloat16*)out_bf16, row_map, M, C, eps);
+    D3R_CUDA(pdl::launch(layernorm_kernel<8>, dim3(blocks), dim3(warps * 32), 0, st, x, g, b, (__nv_bfloat16*)out_bf16, row_map, M, C, eps));
   else
-    layernorm_kernel<16><<<blocks, warps * 32, 0, st>>>(x, g, b, (__nv_bfloat16*)out_bf16, row_map, M, C, eps);
+    D3R_CUDA(pdl::launch(layernorm_kernel<16>, dim3(blocks), dim3(warps * 32), 0, st, x, g, b, (__nv_bfloat16*)out_bf16, row_map, M, C, eps));
   D3R_LAUNCH_CHECK();
   return D3R_OK;
 }
 
 // ---- fp32 -> bf16 cast ----------------------------------------------------------------------------
 __global__ void cast_kernel(const float4* __restrict__ x, uint2* __restrict__ o, size_t n4) {
+  pdl::sync_with_predecessor();   // PDL: nothing above touches memory produced by other kernels
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n4) {
     const float4 v = x[i];
@@ -91,7 +94,7 @@ int cast_f32_bf16(const float* x, void* out, size_t n, cudaStream_t st) {
   const size_t n4 = n / 4;
   if (n4 == 0) return D3R_OK;
   prof::Scope scope("cast_f32_bf16", st, 0.0, double(n) * 6.0);
-  cast_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>((const float4*)x, (uint2*)out, n4);
+  D3R_CUDA(pdl::launch(cast_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st, (const float4*)x, (uint2*)out, n4));
   D3R_LAUNCH_CHECK();
   return D3R_OK;
 }
@@ -99,6 +102,7 @@ int cast_f32_bf16(const float* x, void* out, size_t n, cudaStream_t st) {
 // ---- gather rows of a bf16 matrix: out[r] = in[map[r / rows_per] * rows_per + r % rows_per] -------
 __global__ void gather_rows_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const int* __restrict__ img_map,
                                    int rows_per_img, int vec_per_row, size_t total) {
+  pdl::sync_with_predecessor();   // PDL: nothing above touches memory produced by other kernels
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const size_t row = i / vec_per_row;
@@ -113,7 +117,7 @@ int gather_images_bf16(const void* in, void* out, const int* img_map_dev, int n_
   const size_t total = (size_t)n_out_imgs * rows_per_img * vpr;
   if (!total) return D3R_OK;
   prof::Scope scope("gather_images", st, 0.0, double(total) * 32.0);
-  gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const uint4*)in, (uint4*)out, img_map_dev, rows_per_img, vpr, total);
+  D3R_CUDA(pdl::launch(gather_rows_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, (const uint4*)in, (uint4*)out, img_map_dev, rows_per_img, vpr, total));
   D3R_LAUNCH_CHECK();
   return D3R_OK;
 }
@@ -121,6 +125,7 @@ int gather_images_bf16(const void* in, void* out, const int* img_map_dev, int n_
 // ---- patch im2col: (B,3,H,W) fp32 -> [B*gh*gw][3*P*P] bf16, k = c*P*P + py*P + px (Conv2d weight flatten)
 __global__ void patch_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int H, int W,
                                     int gh, int gw) {
+  pdl::sync_with_predecessor();   // PDL: nothing above touches memory produced by other kernels
   // one thread per (token, c, py): 16 contiguous pixels
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)B * gh * gw * 48;
@@ -141,7 +146,7 @@ int patch_im2col16(const float* img, void* out, int B, int H, int W, cudaStream_
   D3R_CHECK_ARG(H % 16 == 0 && W % 16 == 0, "patch_im2col: image %dx%d is not a multiple of the 16-pixel patch", H, W);
   const size_t total = (size_t)B * (H / 16) * (W / 16) * 48;
   prof::Scope scope("patch_im2col", st, 0.0, double(total) * 96.0);
-  patch_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(img, (__nv_bfloat16*)out, B, H, W, H / 16, W / 16);
+  D3R_CUDA(pdl::launch(patch_im2col_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, img, (__nv_bfloat16*)out, B, H, W, H / 16, W / 16));
   D3R_LAUNCH_CHECK();
   return D3R_OK;
 }
@@ -149,6 +154,7 @@ int patch_im2col16(const float* img, void* out, int B, int H, int W, cudaStream_
 // ---- bilinear x2 upsample, align_corners=True, NHWC bf16 (F.interpolate in dpt_block.py:226,247) ----
 __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                           int H, int W, int C, int Ho, int Wo, int vpc_shift) {
+  pdl::sync_with_predecessor();   // PDL: nothing above touches memory produced by other kernels
   // grid = (x tiles, Ho, B): the row interpolation terms are block-uniform, no per-thread div/mod chain
   const int oy = blockIdx.y, b = blockIdx.z;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -192,7 +198,7 @@ int upsample2x_bf16(const void* x, void* out, int B, int H, int W, int C, int Ho
   const size_t total = (size_t)B * Ho * Wo * vpc;
   prof::Scope scope("upsample2x", st, 0.0, double(total) * 20.0);
   dim3 grid((unsigned)(((size_t)Wo * vpc + 255) / 256), (unsigned)Ho, (unsigned)B);
-  upsample2x_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, H, W, C, Ho, Wo, shift);
+  D3R_CUDA(pdl::launch(upsample2x_kernel, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)out, H, W, C, Ho, Wo, shift));
   D3R_LAUNCH_CHECK();
   return D3R_OK;
 }
@@ -200,6 +206,7 @@ int upsample2x_bf16(const void* x, void* out, int B, int H, int W, int C, int Ho
 // ---- im2col for the one strided conv (3x3, stride 2, pad 1): (B,H,W,C) -> [B*Ho*Wo][9*C] ------------
 __global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int H, int W,
                                  int C, int Ho, int Wo) {
+  pdl::sync_with_predecessor();   // PDL: nothing above touches memory produced by other kernels
   const int vpc = C / 8;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)B * Ho * Wo * 9 * vpc;
@@ -222,7 +229,7 @@ int im2col_3x3_s2_bf16(const void* x, void* out, int B, int H, int W, int C, cud
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const size_t total = (size_t)B * Ho * Wo * 9 * (C / 8);
   prof::Scope scope("im2col_s2", st, 0.0, double(total) * 32.0);
-  im2col_s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, B, H, W, C, Ho, Wo);
+  D3R_CUDA(pdl::launch(im2col_s2_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)out, B, H, W, C, Ho, Wo));
   D3R_LAUNCH_CHECK();
   return D3R_OK;
 }
@@ -245,6 +252,7 @@ __device__ __forceinline__ void post_one(float x, float y, float z, float c, flo
 // linear head: feat [B*gh*gw][nch*256] fp32, channel-major then (py,px)  -> pixel shuffle -> postprocess
 __global__ void linear_head_post_kernel(const float* __restrict__ feat, float* __restrict__ pts3d, float* __restrict__ conf,
                                         int B, int gh, int gw, int nch, int depth_mode, int conf_mode, float cmin, float cmax) {
+  pdl::sync_with_predecessor();   // PDL: nothing above touches memory produced by other kernels
   const int H = gh * 16, W = gw * 16;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)B * H * W) return;
@@ -262,7 +270,7 @@ int linear_head_postprocess(const float* feat, float* pts3d, float* conf, int B,
                             int conf_mode, float cmin, float cmax, cudaStream_t st) {
   const size_t total = (size_t)B * gh * gw * 256;
   prof::Scope scope("linear_head_post", st, 0.0, double(total) * 32.0);
-  linear_head_post_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(feat, pts3d, conf, B, gh, gw, nch, depth_mode, conf_mode, cmin, cmax);
+  D3R_CUDA(pdl::launch(linear_head_post_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, feat, pts3d, conf, B, gh, gw, nch, depth_mode, conf_mode, cmin, cmax));
   D3R_LAUNCH_CHECK();
   return D3R_OK;
 }

@@ -67,7 +67,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   char detail[96];
   snprintf(detail, sizeof(detail), "M=%d N=%d K=%d flags=0x%x mode=%d epi=%d", p.M, p.N, p.K, (unsigned)p.flags, p.mode, EPI);
   prof::Scope scope(tag, st, 2.0 * double(p.M) * double(p.N) * double(p.K), 0.0, 1, detail);
-  gemm_kernel<BN, EPI><<<grid, kNumThreads, Cfg<BN, EPI>::kSmemBytes, st>>>(ta, tb, to, p);
+  D3R_CUDA(pdl::launch(gemm_kernel<BN, EPI>, dim3(grid), dim3(kNumThreads), size_t(Cfg<BN, EPI>::kSmemBytes), st, ta, tb, to, p));
   D3R_LAUNCH_CHECK();
   return D3R_OK;
 }
@@ -97,7 +97,7 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   char detail[96];
   snprintf(detail, sizeof(detail), "M=%d N=%d K=%d flags=0x%x mode=%d epi=%d", p.M, p.N, p.K, (unsigned)p.flags, p.mode, EPI);
   prof::Scope scope(tag, st, 2.0 * double(p.M) * double(p.N) * double(p.K), 0.0, 1, detail);
-  gemm2_kernel<BN, EPI><<<2 * clusters, kNumThreads, Cfg2<BN, EPI>::kSmemBytes, st>>>(ta, tb, to, p);
+  D3R_CUDA(pdl::launch(gemm2_kernel<BN, EPI>, dim3(2 * clusters), dim3(kNumThreads), size_t(Cfg2<BN, EPI>::kSmemBytes), st, ta, tb, to, p));
   D3R_LAUNCH_CHECK();
   return D3R_OK;
 }

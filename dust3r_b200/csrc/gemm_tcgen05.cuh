@@ -21,6 +21,7 @@
 #pragma once
 #include "d3r_common.cuh"
 #include "sm100_ptx.cuh"
+#include "pdl.cuh"
 
 namespace d3r {
 namespace gemm {
@@ -199,6 +200,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl::sync_with_predecessor();   // set-up done (weights-only reads so far); A / residual / addends come from other kernels
 
   if (warp == 0) {
     // ================= TMA producer =================
