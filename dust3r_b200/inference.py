@@ -144,33 +144,71 @@ def inference(pairs, model, device, batch_size=8, verbose=True, keep_on_device=F
     mb = _micro_batch(batch_size)
     r0 = 0
     pending = []
+    # pair lists from make_pairs reuse the same image dict in many pairs (n images -> up to n(n-1) pairs): upload every
+    # distinct image once and let each batch address the ones it needs through index maps -- the encoder then runs once
+    # per distinct image of a batch instead of twice per pair (its output for an image does not depend on what else
+    # is in the batch, so results are unchanged)
+    uniq_dev, gidx = None, ([], [])
+    if hasattr(model, 'forward_indexed') and all(int(v['img'].shape[0]) == 1 for vs in views for v in vs):
+        uniq, order = {}, []
+        for k in range(2):
+            for v in views[k]:
+                t = v['img']
+                key = (t.data_ptr(), tuple(t.shape), tuple(t.stride()))
+                if key not in uniq:
+                    uniq[key] = len(order)
+                    order.append(t)
+                gidx[k].append(uniq[key])
+        if len(order) < 2 * n:
+            uniq_dev = torch.empty((len(order),) + tuple(order[0].shape[1:]), dtype=order[0].dtype, device=dev)
+            up.wait_stream(main)
+            with torch.cuda.stream(up):
+                if all(t.is_pinned() for t in order):
+                    for j, t in enumerate(order):
+                        uniq_dev[j:j + 1].copy_(t, non_blocking=True)
+                else:
+                    stage = torch.empty(uniq_dev.shape, dtype=uniq_dev.dtype, pin_memory=True)
+                    _fill_pinned(stage, order, 0, wait=True)
+                    uniq_dev.copy_(stage, non_blocking=True)
+            ev_uniq = torch.cuda.Event()
+            ev_uniq.record(up)
+            main.wait_event(ev_uniq)
     for i in tqdm.trange(0, n, mb, disable=not verbose):
         chunk = (views[0][i:i + mb], views[1][i:i + mb])
         r1 = r0
         srcs = [[v['img'] for v in chunk[k]] for k in range(2)]
         direct = all(t.is_pinned() for ts in srcs for t in ts)
+        indexed = uniq_dev is not None
         for k in range(2):
             # sources already in pinned memory are uploaded straight from where they are; the collated copy that the
             # caller gets back is then filled in the background, off the critical path
-            r1, futs = _fill_pinned(img_pin[k], srcs[k], r0, wait=not direct)
+            r1, futs = _fill_pinned(img_pin[k], srcs[k], r0, wait=not (direct or indexed))
             pending.extend(futs)
         _mark('fill')
-        with torch.cuda.stream(up):
-            for k in range(2):
-                if direct:
-                    r = r0
-                    for t in srcs[k]:
-                        img_dev[k][r:r + int(t.shape[0])].copy_(t, non_blocking=True)
-                        r += int(t.shape[0])
-                else:
-                    img_dev[k][r0:r1].copy_(img_pin[k][r0:r1], non_blocking=True)
-        ev_up = torch.cuda.Event()
-        ev_up.record(up)
-        main.wait_event(ev_up)
-        d = [dict({key: collate_with_cat([v[key] for v in chunk[k]]) for key in chunk[k][0] if key != 'img'},
-                  img=img_dev[k][r0:r1]) for k in range(2)]
-        _mark('h2d+meta')
-        pred1, pred2 = model(d[0], d[1])
+        if indexed:
+            g1, g2 = gidx[0][i:i + mb], gidx[1][i:i + mb]
+            ids = sorted(set(g1) | set(g2))
+            loc = {g: j for j, g in enumerate(ids)}
+            sel = uniq_dev if len(ids) == uniq_dev.shape[0] else uniq_dev.index_select(0, torch.tensor(ids, device=dev))
+            _mark('h2d+meta')
+            pred1, pred2 = model.forward_indexed(sel, [loc[g] for g in g1], [loc[g] for g in g2])
+        else:
+            with torch.cuda.stream(up):
+                for k in range(2):
+                    if direct:
+                        r = r0
+                        for t in srcs[k]:
+                            img_dev[k][r:r + int(t.shape[0])].copy_(t, non_blocking=True)
+                            r += int(t.shape[0])
+                    else:
+                        img_dev[k][r0:r1].copy_(img_pin[k][r0:r1], non_blocking=True)
+            ev_up = torch.cuda.Event()
+            ev_up.record(up)
+            main.wait_event(ev_up)
+            d = [dict({key: collate_with_cat([v[key] for v in chunk[k]]) for key in chunk[k][0] if key != 'img'},
+                      img=img_dev[k][r0:r1]) for k in range(2)]
+            _mark('h2d+meta')
+            pred1, pred2 = model(d[0], d[1])
         _mark('forward-enqueued')
         flat = {('pred1', k): v for k, v in pred1.items()}
         flat.update({('pred2', k): v for k, v in pred2.items()})

@@ -229,6 +229,25 @@ class AsymmetricCroCo3DStereo(nn.Module, _HubMixin, **_hub_kwargs):
         return res1, res2
 
 
+    def forward_indexed(self, imgs, idx1, idx2):
+        """Extension used by inference(): `imgs` (n,3,H,W) are the DISTINCT images of a batch (CUDA), pair b is
+        (imgs[idx1[b]], imgs[idx2[b]]).  The encoder runs once per distinct image (the reference encodes every pair's
+        two images again, model.py:142-170; a symmetrised batch is the special case it shortcuts); decoder and heads
+        run per pair.  Same outputs as forward() on the expanded batch."""
+        dev = imgs.device
+        _lib.require_cuda_device(dev)
+        if self._packed is None or self._packed.device != dev:
+            if next(self.parameters()).device != dev:
+                raise _lib.D3RError(f'model parameters live on {next(self.parameters()).device}, images on {dev}')
+            self.repack()
+        B = len(idx1)
+        assert len(idx2) == B and B > 0
+        H, W = int(imgs.shape[-2]), int(imgs.shape[-1])
+        res1, res2 = self._packed.forward(imgs.float().contiguous(), np.asarray(idx1, dtype=np.int32), np.asarray(idx2, dtype=np.int32), B, H, W)
+        res2['pts3d_in_other_view'] = res2.pop('pts3d')
+        return res1, res2
+
+
 class _PackedModel:
     """Device-side operand buffers + the ctypes `d3r_model` descriptor pointing at them."""
 

@@ -129,6 +129,14 @@ def test_inference_pipelined_micro_batches_bit_identical(cuda_device):
         assert torch.equal(a['view1']['img'], b['view1']['img']) and torch.equal(a['view2']['img'], torch.cat([p[1]['img'] for p in pairs]))
         for which, key in (('pred1', 'pts3d'), ('pred1', 'conf'), ('pred2', 'pts3d_in_other_view'), ('pred2', 'conf')):
             assert torch.equal(a[which][key], b[which][key]), (sym, which, key)
+        # make_pairs shares one image dict between many pairs -> inference() encodes each distinct image once per
+        # batch (index maps).  With private copies of every image it falls back to encoding both images of every
+        # pair, like the reference: the two must agree bit for bit.
+        private = [(dict(x, img=x['img'].clone()), dict(y, img=y['img'].clone())) for x, y in pairs]
+        c = inference(private, net, cuda_device, batch_size=16, verbose=False)
+        for which, key in (('pred1', 'pts3d'), ('pred1', 'conf'), ('pred2', 'pts3d_in_other_view'), ('pred2', 'conf')):
+            assert torch.equal(a[which][key], c[which][key]), ('private copies', sym, which, key)
+        assert torch.equal(a['view1']['img'], c['view1']['img'])
 
 
 @pytest.mark.timeout(900)
