@@ -1,88 +1,55 @@
-"""Host glue of the forward path (API mirror of dust3r/utils/misc.py:10-121)."""
+"""Small host-side helpers of the forward path.
+
+Only `is_symmetrized` carries reference semantics that the fused forward depends on (dust3r/utils/misc.py:32-40
+decides, from the `instance` strings of a batch, whether it has the layout [(a,b),(b,a),(c,d),(d,c),...] whose
+encoder work can be halved).  The head wrappers of the reference (`transpose_to_landscape`) have no counterpart here:
+token-grid handling lives inside the fused C call (`d3r_forward_pairs`)."""
 from __future__ import annotations
+
+import inspect
 
 import torch
 
 
-def fill_default_args(kwargs, func):
-    import inspect
-    for k, v in inspect.signature(func).parameters.items():
-        if v.default is not inspect.Parameter.empty:
-            kwargs.setdefault(k, v.default)
+def is_symmetrized(view1, view2) -> bool:
+    """A batch is symmetrised when consecutive pairs mirror each other: instance1[2k] == instance2[2k+1] and
+    instance1[2k+1] == instance2[2k] for every k.  One pair alone never counts.  An odd batch whose complete couples
+    all mirror runs off the end in the reference (IndexError); that quirk is kept, a mismatch found earlier simply
+    answers False."""
+    first, second = view1['instance'], view2['instance']
+    n = len(first)
+    if n == len(second) == 1:
+        return False
+    for k in range(0, n, 2):
+        if k + 1 >= n:
+            raise IndexError('is_symmetrized: odd batch of mirrored couples')
+        if first[k] != second[k + 1] or first[k + 1] != second[k]:
+            return False
+    return True
+
+
+def freeze_all_params(modules) -> None:
+    """requires_grad = False on every parameter of the given modules (plain tensors/parameters are accepted too)."""
+    for mod in modules:
+        params = mod.parameters() if isinstance(mod, torch.nn.Module) else [mod]
+        for prm in params:
+            prm.requires_grad_(False)
+
+
+def fill_default_args(kwargs: dict, func) -> dict:
+    """Complete `kwargs` in place with the defaults declared by `func`'s signature."""
+    defaults = {name: prm.default for name, prm in inspect.signature(func).parameters.items()
+                if prm.default is not inspect.Parameter.empty}
+    for name, value in defaults.items():
+        kwargs.setdefault(name, value)
     return kwargs
 
 
-def freeze_all_params(modules):
-    for module in modules:
-        try:
-            for n, param in module.named_parameters():
-                param.requires_grad = False
-        except AttributeError:
-            module.requires_grad = False
-
-
-def is_symmetrized(gt1, gt2):
-    """True when the batch is [(a,b),(b,a),(c,d),(d,c),...] judged on the `instance` strings;
-    a batch of one pair is never symmetrised (misc.py:32-40)."""
-    x, y = gt1['instance'], gt2['instance']
-    if len(x) == len(y) and len(x) == 1:
-        return False
-    ok = True
-    for i in range(0, len(x), 2):
-        ok = ok and (x[i] == y[i + 1]) and (x[i + 1] == y[i])
-    return ok
-
-
-def flip(tensor):
-    return torch.stack((tensor[1::2], tensor[0::2]), dim=1).flatten(0, 1)
-
-
-def interleave(tensor1, tensor2):
-    res1 = torch.stack((tensor1, tensor2), dim=1).flatten(0, 1)
-    res2 = torch.stack((tensor2, tensor1), dim=1).flatten(0, 1)
-    return res1, res2
-
-
-def transposed(dic):
-    return {k: v.swapaxes(1, 2) for k, v in dic.items()}
-
-
-def transpose_to_landscape(head, activate=True):
-    """Wrap a head so portrait images are predicted in landscape and transposed back (misc.py:54-100)."""
-    def wrapper_no(decout, true_shape):
-        assert true_shape[0:1].allclose(true_shape), 'true_shape must be all identical'
-        H, W = true_shape[0].cpu().tolist()
-        return head(decout, (H, W))
-
-    def wrapper_yes(decout, true_shape):
-        B = len(true_shape)
-        H, W = int(true_shape.min()), int(true_shape.max())
-        height, width = true_shape.T
-        is_landscape = (width >= height)
-        is_portrait = ~is_landscape
-        if is_landscape.all():
-            return head(decout, (H, W))
-        if is_portrait.all():
-            return transposed(head(decout, (W, H)))
-
-        def selout(ar): return [d[ar] for d in decout]
-        l_result = head(selout(is_landscape), (H, W))
-        p_result = transposed(head(selout(is_portrait), (W, H)))
-        result = {}
-        for k in l_result | p_result:
-            x = l_result[k].new_empty((B,) + tuple(l_result[k].shape[1:]))
-            x[is_landscape] = l_result[k]
-            x[is_portrait] = p_result[k]
-            result[k] = x
-        return result
-
-    return wrapper_yes if activate else wrapper_no
-
-
-def invalid_to_nans(arr, valid_mask, ndim=999):
-    if valid_mask is not None:
-        arr = arr.clone()
-        arr[~valid_mask] = float('nan')
-    if arr.ndim > ndim:
-        arr = arr.flatten(-2 - (arr.ndim - ndim), -2)
-    return arr
+def interleave(x, y):
+    """(x0,y0,x1,y1,...) and (y0,x0,y1,x1,...) along dim 0 -- how a batch is symmetrised on the fly."""
+    n = x.shape[0]
+    a = torch.empty((2 * n,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    b = torch.empty_like(a)
+    a[0::2], a[1::2] = x, y
+    b[0::2], b[1::2] = y, x
+    return a, b
