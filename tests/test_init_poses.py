@@ -83,3 +83,50 @@ def test_mst_init_matches_reference():
             b = torch.cat((qb * sign, b[:, 4:]), dim=-1)
         assert torch.allclose(a, b, atol=2e-3, rtol=2e-3), (k, float((a - b).abs().max()))
     assert torch.allclose(ref.im_depthmaps.data, net.im_depthmaps.data, atol=2e-3, rtol=2e-3)
+
+
+@pytest.mark.skipif(not has_reference(), reason='reference not mounted')
+def test_pair_viewer_matches_live_reference():
+    """GlobalAlignerMode.PairViewer (closed form, cv2 PnP) against the unmodified reference class on a consistent
+    two-view scene, OpenCV's RANSAC seeded identically."""
+    import cv2
+    sys.path.insert(0, os.path.join(ROOT, 'oracle', 'roma_stub'))
+    sys.path.insert(0, '/root/reference')
+    from dust3r_b200.cloud_opt import global_aligner as ours, GlobalAlignerMode as OurMode
+    from dust3r.cloud_opt import global_aligner as theirs, GlobalAlignerMode as RefMode
+    out, cams, f = synth_consistent_scene(2, [(0, 1), (1, 0)], 48, 64, seed=3, noise=0.002)
+    cv2.setRNGSeed(0)
+    a = ours(copy.deepcopy(out), 'cpu', mode=OurMode.PairViewer, verbose=False)
+    cv2.setRNGSeed(0)
+    b = theirs(copy.deepcopy(out), 'cpu', mode=RefMode.PairViewer, verbose=False)
+    assert torch.allclose(a.get_focals(), b.get_focals(), rtol=1e-6)
+    assert torch.allclose(a.get_im_poses(), b.get_im_poses(), atol=1e-5)
+    assert torch.equal(a.get_principal_points(), b.get_principal_points())
+    assert torch.allclose(a.get_intrinsics(), b.get_intrinsics(), rtol=1e-6)
+    for x, y in zip(a.get_depthmaps(), b.get_depthmaps()):
+        assert torch.allclose(x, y, atol=1e-5)
+    for x, y in zip(a.get_pts3d(), b.get_pts3d()):
+        assert torch.allclose(x, y, atol=1e-5)
+    for x, y in zip(a.get_masks(), b.get_masks()):
+        assert torch.equal(x, y)
+    assert np.isnan(a())   # no objective: forward() is NaN like the reference's
+
+
+@pytest.mark.skipif(not has_reference(), reason='reference not mounted')
+def test_is_symmetrized_quirks_match_live_reference():
+    """Exhaustive over instance lists of length <= 5 on a two-letter alphabet, including the IndexError the reference
+    raises for an odd batch of mirrored couples."""
+    import itertools
+    sys.path.insert(0, '/root/reference')
+    from dust3r.utils.misc import is_symmetrized as ref
+    from dust3r_b200.utils.misc import is_symmetrized as mine
+
+    def outcome(fn, a, b):
+        try:
+            return bool(fn(dict(instance=a), dict(instance=b)))
+        except IndexError:
+            return 'IndexError'
+    for n in range(1, 6):
+        for a in itertools.product('ab', repeat=n):
+            for b in itertools.product('ab', repeat=n):
+                assert outcome(mine, list(a), list(b)) == outcome(ref, list(a), list(b)), (a, b)
