@@ -50,116 +50,121 @@ class ModularPointCloudOptimizer(BasePCOptimizer):
             self.pw_adaptors.data.copy_(s['pw_adaptors'])
         return pull
 
-    # ---------------------------------------------------------------- presets
-    def preset_pose(self, known_poses, pose_msk=None):
-        if isinstance(known_poses, torch.Tensor) and known_poses.ndim == 2:
-            known_poses = [known_poses]
-        for idx, pose in zip(self._get_msk_indices(pose_msk), known_poses):
+    # ---------------------------------------------------------------- fixing parameters to known values
+    # A preset writes the value into the per-image parameter and switches its gradient off; the fused step receives the
+    # flags as its trainable mask (see _engine_push), so a preset image keeps exactly the value given here.
+    def _select(self, msk):
+        """Image indices addressed by `msk`: None = all, an int, a list / array / tensor of ints, or a boolean mask."""
+        if msk is None:
+            return list(range(self.n_imgs))
+        if isinstance(msk, (int, np.integer)):
+            return [int(msk)]
+        arr = msk.detach().cpu().numpy() if torch.is_tensor(msk) else np.asarray(msk)
+        if arr.dtype == np.bool_:
+            assert len(arr) == self.n_imgs
+            return np.flatnonzero(arr).tolist()
+        if np.issubdtype(arr.dtype, np.integer):
+            return arr.reshape(-1).tolist()
+        raise ValueError(f'bad {msk=}')
+
+    _get_msk_indices = _select   # reference name
+
+    def _preset(self, what, setter, values, msk):
+        for idx, value in zip(self._select(msk), values):
             if self.verbose:
-                print(f' (setting pose #{idx} = {pose[:3,3]})')
-            self._no_grad(self._set_pose(self.im_poses, idx, torch.as_tensor(pose), force=True))
-        n_known_poses = sum((p.requires_grad is False) for p in self.im_poses)
-        self.norm_pw_scale = (n_known_poses <= 1)
+                shown = value[:3, 3] if what == 'pose' else value
+                print(f' (setting {what} #{idx} = {shown})')
+            setter(idx, value).requires_grad_(False)
+
+    def preset_pose(self, known_poses, pose_msk=None):
+        if torch.is_tensor(known_poses) and known_poses.ndim == 2:
+            known_poses = [known_poses]
+        self._preset('pose', lambda i, pose: self._set_pose(self.im_poses, i, torch.as_tensor(pose), force=True), known_poses,
+                     pose_msk)
+        # with two or more cameras pinned the global scale is no longer a free gauge: stop normalising pairwise scales
+        frozen = sum(1 for prm in self.im_poses if not prm.requires_grad)
+        self.norm_pw_scale = frozen <= 1
+
+    def preset_focal(self, known_focals, msk=None):
+        self._preset('focal', lambda i, f: self._set_focal(i, f, force=True), known_focals, msk)
+
+    def preset_principal_point(self, known_pp, msk=None):
+        self._preset('principal point', lambda i, pp: self._set_principal_point(i, pp, force=True), known_pp, msk)
 
     def preset_intrinsics(self, known_intrinsics, msk=None):
-        if isinstance(known_intrinsics, torch.Tensor) and known_intrinsics.ndim == 2:
+        if torch.is_tensor(known_intrinsics) and known_intrinsics.ndim == 2:
             known_intrinsics = [known_intrinsics]
-        for K in known_intrinsics:
-            assert K.shape == (3, 3)
+        assert all(tuple(K.shape) == (3, 3) for K in known_intrinsics)
         self.preset_focal([K.diagonal()[:2].mean() for K in known_intrinsics], msk)
         self.preset_principal_point([K[:2, 2] for K in known_intrinsics], msk)
 
-    def preset_focal(self, known_focals, msk=None):
-        for idx, focal in zip(self._get_msk_indices(msk), known_focals):
-            if self.verbose:
-                print(f' (setting focal #{idx} = {focal})')
-            self._no_grad(self._set_focal(idx, focal, force=True))
+    # ---------------------------------------------------------------- parameterisation
+    # focal = exp(param / focal_brake) (one or two entries per image), principal point = image centre + 10 * param,
+    # depth = exp(param); a setter only writes when the parameter is trainable or `force` is given.
+    @staticmethod
+    def _writable(param, force):
+        return force or param.requires_grad
 
-    def preset_principal_point(self, known_pp, msk=None):
-        for idx, pp in zip(self._get_msk_indices(msk), known_pp):
-            if self.verbose:
-                print(f' (setting principal point #{idx} = {pp})')
-            self._no_grad(self._set_principal_point(idx, pp, force=True))
-
-    def _no_grad(self, tensor):
-        return tensor.requires_grad_(False)
-
-    def _get_msk_indices(self, msk):
-        if msk is None:
-            return range(self.n_imgs)
-        if isinstance(msk, int):
-            return [msk]
-        if isinstance(msk, (tuple, list)):
-            return self._get_msk_indices(np.array(msk))
-        if msk.dtype in (bool, torch.bool, np.bool_):
-            assert len(msk) == self.n_imgs
-            return np.where(msk)[0]
-        if np.issubdtype(msk.dtype, np.integer):
-            return msk
-        raise ValueError(f'bad {msk=}')
-
-    # ---------------------------------------------------------------- accessors
     def _set_focal(self, idx, focal, force=False):
         param = self.im_focals[idx]
-        if param.requires_grad or force:
-            param.data[:] = self.focal_brake * np.log(float(focal))
+        if self._writable(param, force):
+            param.data.fill_(self.focal_brake * np.log(float(focal)))
         return param
-
-    def get_focals(self):
-        return (torch.stack(list(self.im_focals), dim=0) / self.focal_brake).exp()
-
-    def get_known_focal_mask(self):
-        return torch.tensor([not p.requires_grad for p in self.im_focals])
 
     def _set_principal_point(self, idx, pp, force=False):
         param = self.im_pp[idx]
-        H, W = self.imshapes[idx]
-        if param.requires_grad or force:
-            param.data[:] = to_cpu(to_numpy(pp) - (W / 2, H / 2)) / 10
+        if self._writable(param, force):
+            H, W = self.imshapes[idx]
+            centre = torch.tensor((W / 2, H / 2), dtype=param.dtype)
+            param.data.copy_((torch.as_tensor(to_numpy(pp), dtype=param.dtype).cpu() - centre) / 10)
         return param
-
-    def get_principal_points(self):
-        return torch.stack([pp.new_tensor((W / 2, H / 2)) + 10 * pp for pp, (H, W) in zip(self.im_pp, self.imshapes)])
-
-    def get_intrinsics(self):
-        K = torch.zeros((self.n_imgs, 3, 3), device=self.device)
-        focals = self.get_focals().view(self.n_imgs, -1)
-        K[:, 0, 0] = focals[:, 0]
-        K[:, 1, 1] = focals[:, -1]
-        K[:, :2, 2] = self.get_principal_points()
-        K[:, 2, 2] = 1
-        return K
-
-    def get_im_poses(self):
-        return self._get_poses(torch.stack(list(self.im_poses)))
 
     def _set_depthmap(self, idx, depth, force=False):
         param = self.im_depthmaps[idx]
-        if param.requires_grad or force:
-            param.data[:] = depth.log().nan_to_num(neginf=0)
+        if self._writable(param, force):
+            param.data.copy_(depth.log().nan_to_num(neginf=0))
         return param
 
+    def get_focals(self):
+        return torch.exp(torch.stack(tuple(self.im_focals)) / self.focal_brake)
+
+    def get_known_focal_mask(self):
+        return torch.tensor([not prm.requires_grad for prm in self.im_focals])
+
+    def get_principal_points(self):
+        centres = torch.tensor([(W / 2, H / 2) for H, W in self.imshapes], dtype=self.im_pp[0].dtype, device=self.im_pp[0].device)
+        return centres + 10 * torch.stack(tuple(self.im_pp))
+
+    def get_intrinsics(self):
+        f = self.get_focals().view(self.n_imgs, -1)     # (n, 1) shared focal or (n, 2) = (fx, fy)
+        K = torch.zeros((self.n_imgs, 3, 3), device=self.device)
+        K[:, 0, 0], K[:, 1, 1], K[:, 2, 2] = f[:, 0], f[:, -1], 1
+        K[:, :2, 2] = self.get_principal_points()
+        return K
+
+    def get_im_poses(self):
+        return self._get_poses(torch.stack(tuple(self.im_poses)))
+
     def get_depthmaps(self):
-        return [d.exp() for d in self.im_depthmaps]
+        return [logd.exp() for logd in self.im_depthmaps]
 
     def depth_to_pts3d(self):
+        """World pointmaps of all images: from the fused step's own unprojection on CUDA, in torch otherwise."""
         if self.device.type == 'cuda':
             eng = self._get_engine()
-            pull = self._engine_push(eng)
-            del pull
-            flat = eng.pts3d()
-            out, off = [], 0
+            self._engine_push(eng)
+            flat, out, off = eng.pts3d(), [], 0
             for H, W in self.imshapes:
                 out.append(flat[off:off + H * W].view(H, W, 3))
                 off += H * W
             return out
-        focals = self.get_focals()
-        pp = self.get_principal_points()
-        im_poses = self.get_im_poses()
-        depth = self.get_depthmaps()
-        def focal_ex(i): return focals[i][..., None, None].expand(1, *focals[i].shape, *self.imshapes[i])
-        rel = [depthmap_to_pts3d(depth[i][None], focal_ex(i), pp=pp[i:i + 1])[0] for i in range(im_poses.shape[0])]
-        return [geotrf(pose, ptmap) for pose, ptmap in zip(im_poses, rel)]
+        focals, pps, poses, depths = self.get_focals(), self.get_principal_points(), self.get_im_poses(), self.get_depthmaps()
+        out = []
+        for i, (H, W) in enumerate(self.imshapes):
+            f_map = focals[i][..., None, None].expand(1, *focals[i].shape, H, W)
+            cam = depthmap_to_pts3d(depths[i][None], f_map, pp=pps[i:i + 1])[0]
+            out.append(geotrf(poses[i], cam))
+        return out
 
     def get_pts3d(self):
         return self.depth_to_pts3d()

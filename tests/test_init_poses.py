@@ -130,3 +130,41 @@ def test_is_symmetrized_quirks_match_live_reference():
         for a in itertools.product('ab', repeat=n):
             for b in itertools.product('ab', repeat=n):
                 assert outcome(mine, list(a), list(b)) == outcome(ref, list(a), list(b)), (a, b)
+
+
+@pytest.mark.skipif(not has_reference(), reason='reference not mounted')
+@pytest.mark.parametrize('fx_and_fy', [False, True])
+def test_modular_optimizer_presets_match_live_reference(fx_and_fy):
+    """Host-side API of ModularPointCloudOptimizer (presets with int / list / boolean-tensor / array masks, parameter
+    encodings, intrinsics, world pointmaps) against the unmodified reference class, same seeds, on the CPU."""
+    import warnings
+    warnings.filterwarnings('ignore')
+    from dust3r_b200.utils.synth import synth_pair_predictions
+    sys.path.insert(0, os.path.join(ROOT, 'oracle', 'roma_stub'))
+    sys.path.insert(0, '/root/reference')
+    from dust3r_b200.cloud_opt import global_aligner as ours, GlobalAlignerMode as OurMode
+    from dust3r.cloud_opt import global_aligner as theirs, GlobalAlignerMode as RefMode
+    n, H, W = 4, 24, 32
+    edges = [(i, j) for i in range(n) for j in range(n) if i != j]
+    out = synth_pair_predictions(n, edges, H, W, seed=2)
+    torch.manual_seed(0)
+    a = ours(copy.deepcopy(out), 'cpu', mode=OurMode.ModularPointCloudOptimizer, verbose=False, fx_and_fy=fx_and_fy, optimize_pp=True)
+    torch.manual_seed(0)
+    b = theirs(copy.deepcopy(out), 'cpu', mode=RefMode.ModularPointCloudOptimizer, verbose=False, fx_and_fy=fx_and_fy, optimize_pp=True)
+    Ks = [torch.tensor([[30. + i, 0, 15 + i], [0, 32. + i, 11 - i], [0, 0, 1.]]) for i in range(2)]
+    poses = [torch.eye(4), torch.tensor([[0., -1, 0, 1], [1, 0, 0, 2], [0, 0, 1, 3], [0, 0, 0, 1]])]
+    for net in (a, b):
+        net.preset_intrinsics(Ks, msk=[1, 3])
+        net.preset_pose(poses, pose_msk=torch.tensor([True, False, True, False]))
+        net.preset_focal([55.0], msk=0)
+        net.preset_principal_point([torch.tensor([14., 13.])], msk=np.array([2]))
+    assert a.norm_pw_scale == b.norm_pw_scale
+    for name in ('im_poses', 'im_pp', 'im_focals'):
+        assert [p.requires_grad for p in getattr(a, name)] == [p.requires_grad for p in getattr(b, name)], name
+    for get in ('get_focals', 'get_principal_points', 'get_intrinsics', 'get_im_poses'):
+        assert torch.equal(getattr(a, get)(), getattr(b, get)()), get
+    for x, y in zip(a.get_pts3d(), b.get_pts3d()):
+        assert torch.equal(x, y)
+    for x, y in zip(a.get_depthmaps(), b.get_depthmaps()):
+        assert torch.equal(x, y)
+    assert a.get_known_focal_mask().tolist() == [True, True, False, True]
