@@ -10,29 +10,32 @@ from __future__ import annotations
 
 from copy import deepcopy
 
-import numpy as np
 import torch
 import torch.nn as nn
 
-from ..utils.geometry import inv, geotrf
+from ..utils.geometry import inv
 from ..utils.image import rgb
-from .commons import (edge_str, ALL_DISTS, NoGradParamDict, get_imshapes, signed_expm1, signed_log1p,
-                      get_conf_trf, unitquat_to_rotmat, rotmat_to_unitquat)
+from . import pose_param
+from .commons import ALL_DISTS, NoGradParamDict, edge_str, get_conf_trf, get_imshapes
 from .engine import AlignEngine
+from .pointcloud_filter import clean_pointcloud
 
 
 class BasePCOptimizer(nn.Module):
     """Graph node = image, graph edge = one pairwise prediction (pred1, pred2).
     Constructor arguments follow base_opt.py:44-53."""
 
+    # attributes shared (not copied) when one optimizer is built from another one
+    _SCENE_ATTRS = ('edges', 'is_symmetrized', 'dist', 'n_imgs', 'pred_i', 'pred_j', 'imshapes', 'min_conf_thr', 'conf_thr',
+                    'conf_i', 'conf_j', 'im_conf', 'base_scale', 'norm_pw_scale', 'POSE_DIM', 'pw_poses', 'pw_adaptors',
+                    'has_im_poses', 'rand_pose', 'imgs', 'verbose')
+
     def __init__(self, *args, **kwargs):
-        if len(args) == 1 and len(kwargs) == 0:
-            other = deepcopy(args[0])
-            attrs = '''edges is_symmetrized dist n_imgs pred_i pred_j imshapes
-                        min_conf_thr conf_thr conf_i conf_j im_conf
-                        base_scale norm_pw_scale POSE_DIM pw_poses
-                        pw_adaptors pw_adaptors has_im_poses rand_pose imgs verbose'''.split()
-            self.__dict__.update({k: other[k] for k in attrs})
+        if len(args) == 1 and not kwargs:
+            # BasePCOptimizer(other): take over a deep copy of the other optimizer's scene (base_opt.py:45-53)
+            source = deepcopy(args[0])
+            for name in self._SCENE_ATTRS:
+                self.__dict__[name] = source[name]
         else:
             self._init_from_views(*args, **kwargs)
 
@@ -40,51 +43,49 @@ class BasePCOptimizer(nn.Module):
                          dist='l1', conf='log', min_conf_thr=3, base_scale=0.5,
                          allow_pw_adaptors=False, pw_break=20, rand_pose=torch.randn,
                          iterationsCount=None, verbose=True):
+        """Scene graph from the output of inference(): view*['idx'] give the image ids of every pair, pred1 / pred2 the
+        two pointmaps (+ confidences) of every pair, both expressed in the first image's camera frame."""
         super().__init__()
-        idx1 = view1['idx'] if isinstance(view1['idx'], list) else view1['idx'].tolist()
-        idx2 = view2['idx'] if isinstance(view2['idx'], list) else view2['idx'].tolist()
-        view1['idx'], view2['idx'] = idx1, idx2
-        self.edges = [(int(i), int(j)) for i, j in zip(idx1, idx2)]
-        self.is_symmetrized = set(self.edges) == {(j, i) for i, j in self.edges}
         if dist not in ALL_DISTS:
             raise KeyError(dist)
-        self.dist = dist
-        self.verbose = verbose
+        self.dist, self.verbose = dist, verbose
+
+        # ---- graph
+        for view in (view1, view2):
+            if not isinstance(view['idx'], list):
+                view['idx'] = view['idx'].tolist()
+        first, second = view1['idx'], view2['idx']
+        self.edges = [(int(i), int(j)) for i, j in zip(first, second)]
+        self.is_symmetrized = {(j, i) for i, j in self.edges} == set(self.edges)
         self.n_imgs = self._check_edges()
 
-        pts1, pts2 = pred1['pts3d'], pred2['pts3d_in_other_view']
-        keys = self.str_edges
-        self.pred_i = NoGradParamDict({ij: pts1[n] for n, ij in enumerate(keys)})
-        self.pred_j = NoGradParamDict({ij: pts2[n] for n, ij in enumerate(keys)})
-        self.imshapes = get_imshapes(self.edges, pts1, pts2)
-
-        c1, c2 = pred1['conf'], pred2['conf']
+        # ---- observations, one entry per directed pair "i_j"
+        def per_edge(stacked):
+            return NoGradParamDict({key: stacked[e] for e, key in enumerate(self.str_edges)})
+        pts_i, pts_j = pred1['pts3d'], pred2['pts3d_in_other_view']
+        self.pred_i, self.pred_j = per_edge(pts_i), per_edge(pts_j)
+        self.imshapes = get_imshapes(self.edges, pts_i, pts_j)
         self.min_conf_thr = min_conf_thr
-        self.conf_mode = conf
-        self.conf_trf = get_conf_trf(conf)
-        self.conf_i = NoGradParamDict({ij: c1[n] for n, ij in enumerate(keys)})
-        self.conf_j = NoGradParamDict({ij: c2[n] for n, ij in enumerate(keys)})
-        self.im_conf = self._compute_img_conf(c1, c2)
-        for p in self.im_conf:
-            p.requires_grad = False
+        self.conf_mode, self.conf_trf = conf, get_conf_trf(conf)
+        self.conf_i, self.conf_j = per_edge(pred1['conf']), per_edge(pred2['conf'])
+        self.im_conf = self._compute_img_conf(pred1['conf'], pred2['conf'])
+        self.im_conf.requires_grad_(False)
 
-        self.base_scale = base_scale
-        self.norm_pw_scale = True
-        self.pw_break = pw_break
+        # ---- pairwise similarity transforms (pose + log-scale) and optional anisotropic adaptors
+        self.base_scale, self.norm_pw_scale, self.pw_break = base_scale, True, pw_break
         self.POSE_DIM = 7
-        self.pw_poses = nn.Parameter(rand_pose((self.n_edges, 1 + self.POSE_DIM)))
-        self.pw_adaptors = nn.Parameter(torch.zeros((self.n_edges, 2)))
-        self.pw_adaptors.requires_grad_(allow_pw_adaptors)
-        self.has_im_poses = False
         self.rand_pose = rand_pose
+        self.pw_poses = nn.Parameter(rand_pose((self.n_edges, 1 + self.POSE_DIM)))
+        self.pw_adaptors = nn.Parameter(torch.zeros((self.n_edges, 2)), requires_grad=bool(allow_pw_adaptors))
+        self.has_im_poses = False
 
+        # ---- colours for visualisation / export
         self.imgs = None
         if 'img' in view1 and 'img' in view2:
-            imgs = [torch.zeros((3,) + hw) for hw in self.imshapes]
-            for v in range(len(self.edges)):
-                imgs[idx1[v]] = view1['img'][v]
-                imgs[idx2[v]] = view2['img'][v]
-            self.imgs = rgb(imgs)
+            canvas = [torch.zeros((3,) + tuple(hw)) for hw in self.imshapes]
+            for e, (i, j) in enumerate(zip(first, second)):
+                canvas[i], canvas[j] = view1['img'][e], view2['img'][e]
+            self.imgs = rgb(canvas)
         self._engine = None
 
     # ---------------------------------------------------------------- bookkeeping
@@ -139,44 +140,33 @@ class BasePCOptimizer(nn.Module):
         return (adapt / self.pw_break).exp()
 
     def _get_poses(self, poses):
-        R = unitquat_to_rotmat(poses[:, :4])
-        T = signed_expm1(poses[:, 4:7])
-        RT = torch.zeros((len(poses), 4, 4), dtype=poses.dtype, device=poses.device)
-        RT[:, :3, :3] = R
-        RT[:, :3, 3] = T
-        RT[:, 3, 3] = 1
-        return RT
+        return pose_param.rows_to_matrices(poses)
 
     def _set_pose(self, poses, idx, R, T=None, scale=None, force=False):
-        pose = poses[idx]
-        if not (pose.requires_grad or force):
-            return pose
-        if R.shape == (4, 4):
+        """Write a rotation / translation (or a 4x4 passed as R) and optionally a scale into pose row `idx`; frozen
+        rows are left alone unless `force`.  Returns the row's parameter."""
+        target = poses[idx]
+        if not (force or target.requires_grad):
+            return target
+        if R is not None and tuple(R.shape) == (4, 4):
             assert T is None
-            T = R[:3, 3]
-            R = R[:3, :3]
-        if R is not None:
-            pose.data[0:4] = rotmat_to_unitquat(R).to(pose.device)
-        if T is not None:
-            pose.data[4:7] = signed_log1p(torch.as_tensor(T / (scale or 1), dtype=torch.float32)).to(pose.device)
+            R, T = pose_param.split_rigid(R)
         if scale is not None:
             assert poses.shape[-1] in (8, 13)
-            pose.data[-1] = np.log(float(scale))
-        return pose
+        pose_param.write_row(target.data, R, T, scale)
+        return target
 
     def get_pw_norm_scale_factor(self):
-        if self.norm_pw_scale:
-            return (np.log(self.base_scale) - self.pw_poses[:, -1].mean()).exp()
-        return 1
+        return pose_param.scale_gauge(self.pw_poses[:, -1], self.base_scale, self.norm_pw_scale)
 
     def get_pw_scale(self):
         return self.pw_poses[:, -1].exp() * self.get_pw_norm_scale_factor()
 
     def get_pw_poses(self):
-        RT = self._get_poses(self.pw_poses)
-        scaled = RT.clone()
-        scaled[:, :3] *= self.get_pw_scale().view(-1, 1, 1)
-        return scaled
+        """(E,4,4) similarity transforms: the rigid part of every pairwise pose with its first three rows scaled."""
+        out = self._get_poses(self.pw_poses).clone()
+        out[:, :3] *= self.get_pw_scale().view(-1, 1, 1)
+        return out
 
     # ---------------------------------------------------------------- accessors
     def get_masks(self):
@@ -308,29 +298,3 @@ def global_alignment_loop(net, lr=0.01, niter=300, schedule='cosine', lr_min=1e-
     if net.verbose:
         print(f' final loss={loss:g} after {niter} iterations')
     return loss
-
-
-@torch.no_grad()
-def clean_pointcloud(im_confs, K, cams, depthmaps, all_pts3d, tol=0.001, bad_conf=0, dbg=()):
-    """Lower the confidence of points that another, more confident view sees *behind* its own depth
-    (base_opt.py:369-405).  O(n^2 P) reprojection test in torch ("next" row f3)."""
-    assert len(im_confs) == len(cams) == len(K) == len(depthmaps) == len(all_pts3d)
-    assert 0 <= tol < 1
-    res = [c.clone() for c in im_confs]
-    all_pts3d = [p.view(*c.shape, 3) for p, c in zip(all_pts3d, im_confs)]
-    depthmaps = [d.view(*c.shape) for d, c in zip(depthmaps, im_confs)]
-    for i, pts3d in enumerate(all_pts3d):
-        for j in range(len(all_pts3d)):
-            if i == j:
-                continue
-            proj = geotrf(cams[j], pts3d)
-            proj_depth = proj[:, :, 2]
-            u, v = geotrf(K[j], proj, norm=1, ncol=2).round().long().unbind(-1)
-            H, W = im_confs[j].shape
-            msk_i = (proj_depth > 0) & (0 <= u) & (u < W) & (0 <= v) & (v < H)
-            msk_j = v[msk_i], u[msk_i]
-            bad_points = (proj_depth[msk_i] < (1 - tol) * depthmaps[j][msk_j]) & (res[i][msk_i] < res[j][msk_j])
-            bad_msk_i = msk_i.clone()
-            bad_msk_i[msk_i] = bad_points
-            res[i][bad_msk_i] = res[i][bad_msk_i].clip_(max=bad_conf)
-    return res
