@@ -1,8 +1,10 @@
-"""global_aligner(): drop-in for dust3r/cloud_opt/__init__.py:14-33."""
+"""Entry point of the alignment path: `global_aligner(dust3r_output, device, mode, **kw)` builds the optimizer object
+for the output of inference() and moves it to `device` (dust3r/cloud_opt/__init__.py:14-33).  The classes keep the
+reference's names and methods; `compute_global_alignment` runs the fused CUDA step (csrc/align_step.cu)."""
 from enum import Enum
 
-from .optimizer import PointCloudOptimizer
 from .modular_optimizer import ModularPointCloudOptimizer
+from .optimizer import PointCloudOptimizer
 from .pair_viewer import PairViewer
 
 
@@ -11,16 +13,15 @@ class GlobalAlignerMode(Enum):
     ModularPointCloudOptimizer = "ModularPointCloudOptimizer"
     PairViewer = "PairViewer"
 
-
-_MODES = {
-    GlobalAlignerMode.PointCloudOptimizer: PointCloudOptimizer,
-    GlobalAlignerMode.ModularPointCloudOptimizer: ModularPointCloudOptimizer,
-    GlobalAlignerMode.PairViewer: PairViewer,
-}
+    @property
+    def optimizer_class(self):
+        return {'PointCloudOptimizer': PointCloudOptimizer, 'ModularPointCloudOptimizer': ModularPointCloudOptimizer,
+                'PairViewer': PairViewer}[self.value]
 
 
 def global_aligner(dust3r_output, device, mode=GlobalAlignerMode.PointCloudOptimizer, **optim_kw):
-    view1, view2, pred1, pred2 = [dust3r_output[k] for k in 'view1 view2 pred1 pred2'.split()]
-    if mode not in _MODES:
+    if not isinstance(mode, GlobalAlignerMode):
         raise NotImplementedError(f'Unknown mode {mode}')
-    return _MODES[mode](view1, view2, pred1, pred2, **optim_kw).to(device)
+    scene = mode.optimizer_class(dust3r_output['view1'], dust3r_output['view2'], dust3r_output['pred1'], dust3r_output['pred2'],
+                                 **optim_kw)
+    return scene.to(device)

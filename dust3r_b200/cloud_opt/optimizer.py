@@ -11,28 +11,30 @@ import torch.nn as nn
 
 from .base_opt import BasePCOptimizer
 from ..utils.geometry import xy_grid, geotrf
-from ..utils.device import to_cpu, to_numpy
+from ..utils.device import to_numpy
 
 
 def _ravel_hw(tensor, fill=0):
-    tensor = tensor.reshape((tensor.shape[0] * tensor.shape[1],) + tuple(tensor.shape[2:]))
-    if len(tensor) < fill:
-        tensor = torch.cat((tensor, tensor.new_zeros((fill - len(tensor),) + tuple(tensor.shape[1:]))))
-    return tensor
+    """(H, W, ...) -> (H*W, ...), zero-padded at the end up to `fill` rows (images of different sizes share one stack)."""
+    flat = tensor.flatten(0, 1)
+    missing = fill - flat.shape[0]
+    if missing > 0:
+        flat = torch.cat((flat, flat.new_zeros((missing,) + tuple(flat.shape[1:]))))
+    return flat
 
 
 def ParameterStack(params, keys=None, is_param=None, fill=0):
-    if keys is not None:
-        params = [params[k] for k in keys]
+    """Stack per-image tensors (optionally picked from a dict by `keys`, optionally flattened + padded to `fill` pixels)
+    into one float tensor; it becomes an nn.Parameter when the inputs were trainable or `is_param` is set."""
+    items = list(params) if keys is None else [params[k] for k in keys]
+    trainable = items[0].requires_grad
+    assert all(it.requires_grad == trainable for it in items)
     if fill > 0:
-        params = [_ravel_hw(p, fill) for p in params]
-    requires_grad = params[0].requires_grad
-    assert all(p.requires_grad == requires_grad for p in params)
-    params = torch.stack(list(params)).float().detach()
-    if is_param or requires_grad:
-        params = nn.Parameter(params)
-        params.requires_grad_(requires_grad)
-    return params
+        items = [_ravel_hw(it, fill) for it in items]
+    stacked = torch.stack(items).float().detach()
+    if is_param or trainable:
+        stacked = nn.Parameter(stacked, requires_grad=trainable)
+    return stacked
 
 
 class PointCloudOptimizer(BasePCOptimizer):
@@ -87,81 +89,85 @@ class PointCloudOptimizer(BasePCOptimizer):
             self.pw_adaptors.data.copy_(s['pw_adaptors'])
         return pull
 
-    # ---------------------------------------------------------------- presets
-    def _check_all_imgs_are_selected(self, msk):
-        assert np.all(self._get_msk_indices(msk) == np.arange(self.n_imgs)), 'incomplete mask!'
-
-    def preset_pose(self, known_poses, pose_msk=None):
-        self._check_all_imgs_are_selected(pose_msk)
-        if isinstance(known_poses, torch.Tensor) and known_poses.ndim == 2:
-            known_poses = [known_poses]
-        for idx, pose in zip(self._get_msk_indices(pose_msk), known_poses):
-            if self.verbose:
-                print(f' (setting pose #{idx} = {pose[:3,3]})')
-            self._no_grad(self._set_pose(self.im_poses, idx, torch.as_tensor(pose)))
-        self.im_poses.requires_grad_(False)
-        self.norm_pw_scale = False
-
-    def preset_focal(self, known_focals, msk=None):
-        self._check_all_imgs_are_selected(msk)
-        for idx, focal in zip(self._get_msk_indices(msk), known_focals):
-            if self.verbose:
-                print(f' (setting focal #{idx} = {focal})')
-            self._no_grad(self._set_focal(idx, focal))
-        self.im_focals.requires_grad_(False)
-
-    def preset_principal_point(self, known_pp, msk=None):
-        self._check_all_imgs_are_selected(msk)
-        for idx, pp in zip(self._get_msk_indices(msk), known_pp):
-            if self.verbose:
-                print(f' (setting principal point #{idx} = {pp})')
-            self._no_grad(self._set_principal_point(idx, pp))
-        self.im_pp.requires_grad_(False)
-
+    # ---------------------------------------------------------------- fixing parameters to known values
+    # The stacked optimizer keeps one tensor per parameter kind, so a preset must cover EVERY image and freezes the
+    # whole kind (use ModularPointCloudOptimizer to pin a subset of the cameras).
     def _get_msk_indices(self, msk):
+        """Image indices addressed by `msk`: None = all, an int, a list / array / tensor of ints, or a boolean mask."""
         if msk is None:
-            return range(self.n_imgs)
-        if isinstance(msk, int):
-            return [msk]
-        if isinstance(msk, (tuple, list)):
-            return self._get_msk_indices(np.array(msk))
-        if msk.dtype in (bool, torch.bool, np.bool_):
-            assert len(msk) == self.n_imgs
-            return np.where(msk)[0]
-        if np.issubdtype(msk.dtype, np.integer):
-            return msk
+            return np.arange(self.n_imgs)
+        if isinstance(msk, (int, np.integer)):
+            return np.array([int(msk)])
+        arr = msk.detach().cpu().numpy() if torch.is_tensor(msk) else np.asarray(msk)
+        if arr.dtype == np.bool_:
+            assert len(arr) == self.n_imgs
+            return np.flatnonzero(arr)
+        if np.issubdtype(arr.dtype, np.integer):
+            return arr.reshape(-1)
         raise ValueError(f'bad {msk=}')
 
-    def _no_grad(self, tensor):
-        assert tensor.requires_grad, 'it must be True at this point, otherwise no modification occurs'
+    def _preset_all(self, what, stacked_param, setter, values, msk):
+        picked = self._get_msk_indices(msk)
+        assert len(picked) == self.n_imgs and np.all(picked == np.arange(self.n_imgs)), 'incomplete mask!'
+        assert stacked_param.requires_grad, 'it must be True at this point, otherwise no modification occurs'
+        for idx, value in zip(picked, values):
+            if self.verbose:
+                shown = value[:3, 3] if what == 'pose' else value
+                print(f' (setting {what} #{idx} = {shown})')
+            setter(int(idx), value)
+        stacked_param.requires_grad_(False)
 
-    # ---------------------------------------------------------------- intrinsics / poses / depth
+    def preset_pose(self, known_poses, pose_msk=None):
+        if torch.is_tensor(known_poses) and known_poses.ndim == 2:
+            known_poses = [known_poses]
+        self._preset_all('pose', self.im_poses, lambda i, pose: self._set_pose(self.im_poses, i, torch.as_tensor(pose)),
+                         known_poses, pose_msk)
+        self.norm_pw_scale = False      # all cameras pinned: the global scale is no longer a free gauge
+
+    def preset_focal(self, known_focals, msk=None):
+        self._preset_all('focal', self.im_focals, self._set_focal, known_focals, msk)
+
+    def preset_principal_point(self, known_pp, msk=None):
+        self._preset_all('principal point', self.im_pp, self._set_principal_point, known_pp, msk)
+
+    # ---------------------------------------------------------------- parameterisation
+    # focal = exp(im_focals / focal_break), principal point = image centre + 10 * im_pp, depth = exp(im_depthmaps);
+    # setters write one image's row and only when the stack is trainable (or `force`).
+    def _row(self, stacked_param, idx, force):
+        row = stacked_param[idx]
+        return row, (force or row.requires_grad)
+
     def _set_focal(self, idx, focal, force=False):
-        param = self.im_focals[idx]
-        if param.requires_grad or force:
-            param.data[:] = self.focal_break * np.log(float(focal))
-        return param
-
-    def get_focals(self):
-        return (self.im_focals / self.focal_break).exp()
-
-    def get_known_focal_mask(self):
-        return torch.tensor([not self.im_focals.requires_grad] * self.n_imgs)
+        row, writable = self._row(self.im_focals, idx, force)
+        if writable:
+            row.data.fill_(self.focal_break * np.log(float(focal)))
+        return row
 
     def _set_principal_point(self, idx, pp, force=False):
-        param = self.im_pp[idx]
-        H, W = self.imshapes[idx]
-        if param.requires_grad or force:
-            param.data[:] = to_cpu(to_numpy(pp) - (W / 2, H / 2)) / 10
-        return param
+        row, writable = self._row(self.im_pp, idx, force)
+        if writable:
+            offset = torch.as_tensor(to_numpy(pp), dtype=row.dtype).cpu() - self._pp[idx].cpu()
+            row.data.copy_(offset / 10)
+        return row
+
+    def _set_depthmap(self, idx, depth, force=False):
+        row, writable = self._row(self.im_depthmaps, idx, force)
+        if writable:
+            row.data.copy_(_ravel_hw(depth, self.max_area).log().nan_to_num(neginf=0))
+        return row
+
+    def get_focals(self):
+        return torch.exp(self.im_focals / self.focal_break)
+
+    def get_known_focal_mask(self):
+        return torch.full((self.n_imgs,), not self.im_focals.requires_grad, dtype=torch.bool)
 
     def get_principal_points(self):
         return self._pp + 10 * self.im_pp
 
     def get_intrinsics(self):
         K = torch.zeros((self.n_imgs, 3, 3), device=self.device)
-        focals = self.get_focals().flatten()
-        K[:, 0, 0] = K[:, 1, 1] = focals
+        K[:, 0, 0] = K[:, 1, 1] = self.get_focals().flatten()
         K[:, :2, 2] = self.get_principal_points()
         K[:, 2, 2] = 1
         return K
@@ -169,31 +175,22 @@ class PointCloudOptimizer(BasePCOptimizer):
     def get_im_poses(self):
         return self._get_poses(self.im_poses)
 
-    def _set_depthmap(self, idx, depth, force=False):
-        depth = _ravel_hw(depth, self.max_area)
-        param = self.im_depthmaps[idx]
-        if param.requires_grad or force:
-            param.data[:] = depth.log().nan_to_num(neginf=0)
-        return param
-
     def get_depthmaps(self, raw=False):
-        res = self.im_depthmaps.exp()
-        if not raw:
-            res = [dm[:h * w].view(h, w) for dm, (h, w) in zip(res, self.imshapes)]
-        return res
+        stack = self.im_depthmaps.exp()
+        if raw:
+            return stack
+        return [row[:h * w].view(h, w) for row, (h, w) in zip(stack, self.imshapes)]
 
     def depth_to_pts3d(self):
         """(n, max_area, 3) world-frame pointmaps.  On a B200 this is one launch of the engine's
         unprojection kernel; before `.to(cuda)` it is evaluated with torch ops (host glue, not timed)."""
         if self.device.type == 'cuda':
             eng = self._get_engine()
-            pull = self._engine_push(eng)
-            del pull
+            self._engine_push(eng)
             return eng.pts3d().view(self.n_imgs, self.max_area, 3)
-        focals = self.get_focals().unsqueeze(1)
-        pp = self.get_principal_points().unsqueeze(1)
+        pixels = torch.stack([_ravel_hw(xy_grid(W, H, device=self.device).float(), self.max_area) for H, W in self.imshapes])
         depth = self.get_depthmaps(raw=True).unsqueeze(-1)
-        grid = torch.stack([_ravel_hw(xy_grid(W, H, device=self.device).float(), self.max_area)
-                            for H, W in self.imshapes])
-        rel = torch.cat((depth * (grid - pp) / focals, depth), dim=-1)
-        return geotrf(self.get_im_poses(), rel)
+        centred = pixels - self.get_principal_points().unsqueeze(1)
+        # (depth * centred) / focal, in this order: bit-identical to the reference's CPU evaluation
+        cam = torch.cat((depth * centred / self.get_focals().unsqueeze(1), depth), dim=-1)
+        return geotrf(self.get_im_poses(), cam)
