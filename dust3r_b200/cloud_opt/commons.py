@@ -1,83 +1,93 @@
-"""Host-side helpers of the global aligner (API mirror of dust3r/cloud_opt/commons.py)."""
+"""Small host-side pieces of the global aligner: edge keys and scores, the confidence transforms, the scalar encodings
+of the pose parameters, the learning-rate schedules (public names as in dust3r/cloud_opt/commons.py), and the three
+rotation / registration routines the reference imports from `roma`."""
 from __future__ import annotations
 
-import numpy as np
+import math
+
 import torch
 import torch.nn as nn
 
 
+# ---- pair graph -------------------------------------------------------------------------------------------------
 def edge_str(i, j):
-    return f'{i}_{j}'
+    """Key of the directed pair (i, j) in the pred_* / conf_* dictionaries."""
+    return '%d_%d' % (i, j) if isinstance(i, int) and isinstance(j, int) else f'{i}_{j}'
 
 
 def i_j_ij(ij):
-    return edge_str(*ij), ij
+    return edge_str(ij[0], ij[1]), ij
 
 
 def edge_conf(conf_i, conf_j, edge):
-    return float(conf_i[edge].mean() * conf_j[edge].mean())
+    """Score of a pair = product of the mean confidences of its two pointmaps."""
+    return float(conf_i[edge].mean()) * float(conf_j[edge].mean())
 
 
 def compute_edge_scores(edges, conf_i, conf_j):
-    return {(i, j): edge_conf(conf_i, conf_j, e) for e, (i, j) in edges}
+    """edges yields (key, (i, j)) couples (see i_j_ij) -> {(i, j): score}."""
+    return {ij: edge_conf(conf_i, conf_j, key) for key, ij in edges}
 
 
 def NoGradParamDict(x):
+    """Tensors registered on the module (they follow .to(device) and land in the state dict) but never trained."""
     assert isinstance(x, dict)
-    return nn.ParameterDict(x).requires_grad_(False)
+    holder = nn.ParameterDict(x)
+    holder.requires_grad_(False)
+    return holder
 
 
 def get_imshapes(edges, pred_i, pred_j):
-    n_imgs = max(max(e) for e in edges) + 1
-    imshapes = [None] * n_imgs
+    """(H, W) of every image, read off the pointmaps of the pairs it takes part in; all of them must agree."""
+    shapes = {}
     for e, (i, j) in enumerate(edges):
-        shape_i = tuple(pred_i[e].shape[0:2])
-        shape_j = tuple(pred_j[e].shape[0:2])
-        if imshapes[i]:
-            assert imshapes[i] == shape_i, f'incorrect shape for image {i}'
-        if imshapes[j]:
-            assert imshapes[j] == shape_j, f'incorrect shape for image {j}'
-        imshapes[i] = shape_i
-        imshapes[j] = shape_j
-    return imshapes
+        for img, pts in ((i, pred_i[e]), (j, pred_j[e])):
+            hw = (int(pts.shape[0]), int(pts.shape[1]))
+            assert shapes.setdefault(img, hw) == hw, f'incorrect shape for image {img}'
+    return [shapes.get(img) for img in range(max(shapes) + 1)]
 
 
+# ---- confidence transform (weight of a residual = trf(confidence)) ---------------------------------------------------
 _CONF_TRF = {
-    'log': lambda x: x.log(),
-    'sqrt': lambda x: x.sqrt(),
-    'm1': lambda x: x - 1,
-    'id': lambda x: x,
-    'none': lambda x: x,
+    'log': torch.log,
+    'sqrt': torch.sqrt,
+    'm1': lambda c: c - 1,
+    'id': lambda c: c,
+    'none': lambda c: c,
 }
 
 
 def get_conf_trf(mode):
-    if mode not in _CONF_TRF:
-        raise ValueError(f'bad mode for {mode=}')
-    return _CONF_TRF[mode]
+    try:
+        return _CONF_TRF[mode]
+    except KeyError:
+        raise ValueError(f'bad mode for {mode=}') from None
 
 
 ALL_DISTS = dict(l1='l1', l2='l2')  # the distances themselves live in the CUDA kernel
 
 
+# ---- scalar encodings ---------------------------------------------------------------------------------------------
 def signed_log1p(x):
-    sign = torch.sign(x)
-    return sign * torch.log1p(torch.abs(x))
+    """sign(x) * log(1 + |x|): translations are optimised in this compressed space."""
+    return torch.copysign(torch.log1p(x.abs()), x) * (x != 0)
 
 
 def signed_expm1(x):
-    sign = torch.sign(x)
-    return sign * torch.expm1(torch.abs(x))
+    """Inverse of signed_log1p."""
+    return torch.copysign(torch.expm1(x.abs()), x) * (x != 0)
 
 
+# ---- learning-rate schedules over t = iteration / niter in [0, 1] -----------------------------------------------------
 def cosine_schedule(t, lr_start, lr_end):
     assert 0 <= t <= 1
-    return lr_end + (lr_start - lr_end) * (1 + np.cos(t * np.pi)) / 2
+    swing = (1 + math.cos(t * math.pi)) / 2          # 1 at t = 0, 0 at t = 1
+    return lr_end + (lr_start - lr_end) * swing
 
 
 def linear_schedule(t, lr_start, lr_end):
     assert 0 <= t <= 1
-    return lr_start + (lr_end - lr_start) * t
+    return lr_start + t * (lr_end - lr_start)
 
 
 # --- rotation helpers the reference takes from `roma` (requirements.txt:3; not a dependency here) ---
