@@ -21,7 +21,7 @@ def i_j_ij(ij):
 
 def edge_conf(conf_i, conf_j, edge):
     """Score of a pair = product of the mean confidences of its two pointmaps."""
-    return float(conf_i[edge].mean()) * float(conf_j[edge].mean())
+    return float(conf_i[edge].mean() * conf_j[edge].mean())     # fp32 product: the ordering of near-ties depends on it
 
 
 def compute_edge_scores(edges, conf_i, conf_j):
