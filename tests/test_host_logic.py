@@ -101,3 +101,51 @@ def test_optimizer_init_matches_reference_draws():
     for a, b in zip(ref.get_pts3d(), net.get_pts3d()):
         assert torch.allclose(a, b, atol=1e-5, rtol=1e-5)
     assert torch.allclose(ref.get_pw_poses(), net.get_pw_poses(), atol=1e-6)
+
+
+def test_geometry_helpers_match_live_reference():
+    """xy_grid / geotrf / inv / depthmap_to_pts3d / depthmap_to_(absolute_)camera_coordinates against the reference's
+    dust3r/utils/geometry.py on random inputs (CPU), every calling convention the two hot paths use."""
+    import pytest
+    from conftest import has_reference
+    if not has_reference():
+        pytest.skip('reference not mounted')
+    import sys
+    import numpy as np
+    import torch
+    sys.path.insert(0, '/root/reference')
+    import dust3r.utils.geometry as ref
+    import dust3r_b200.utils.geometry as mine
+    g = torch.Generator().manual_seed(0)
+    for kw in (dict(), dict(origin=(2, 3)), dict(homogeneous=True), dict(unsqueeze=0), dict(cat_dim=0)):
+        a, b = mine.xy_grid(7, 5, device='cpu', **kw), ref.xy_grid(7, 5, device='cpu', **kw)
+        assert type(a) is type(b) and torch.equal(a, b), kw
+        if 'unsqueeze' not in kw:      # (the reference's numpy branch cannot unsqueeze)
+            a, b = mine.xy_grid(7, 5, **kw), ref.xy_grid(7, 5, **kw)          # device=None -> numpy
+            assert type(a) is type(b) and np.array_equal(a, b), kw
+    T = torch.randn((3, 4, 4), generator=g)
+    T[:, 3] = torch.tensor([0., 0, 0, 1])
+    P = torch.randn((3, 6, 5, 3), generator=g)
+    assert torch.equal(mine.geotrf(T, P), ref.geotrf(T, P))
+    assert torch.equal(mine.geotrf(T[0], P[0]), ref.geotrf(T[0], P[0]))
+    K = torch.tensor([[30., 0, 16], [0, 31, 12], [0, 0, 1]])
+    assert torch.equal(mine.geotrf(K, P[0], norm=1, ncol=2), ref.geotrf(K, P[0], norm=1, ncol=2))
+    assert np.allclose(mine.geotrf(T[0].numpy(), P[0].numpy()), ref.geotrf(T[0].numpy(), P[0].numpy()))
+    assert torch.equal(mine.inv(T), ref.inv(T)) and np.array_equal(mine.inv(T[0].numpy()), ref.inv(T[0].numpy()))
+    depth = torch.rand((2, 6, 5), generator=g) + 0.5
+    for focal in (torch.rand((2, 1, 6, 5), generator=g) + 20, torch.rand((2, 2, 6, 5), generator=g) + 20):
+        pp = torch.tensor([[2.5, 3.0], [2.0, 3.5]])
+        assert torch.equal(mine.depthmap_to_pts3d(depth, focal, pp=pp), ref.depthmap_to_pts3d(depth, focal, pp=pp))
+        assert torch.equal(mine.depthmap_to_pts3d(depth, focal), ref.depthmap_to_pts3d(depth, focal))
+    d = depth[0].numpy()
+    d[0, 0] = 0
+    for fn in ('depthmap_to_camera_coordinates',):
+        xa, ma = getattr(mine, fn)(d, K.numpy())
+        xb, mb = getattr(ref, fn)(d, K.numpy())
+        assert np.array_equal(xa, xb) and np.array_equal(ma, mb)
+    pose = np.eye(4, dtype=np.float32)
+    pose[:3, :3] = np.float32([[0, -1, 0], [1, 0, 0], [0, 0, 1]])
+    pose[:3, 3] = (1, 2, 3)
+    xa, ma = mine.depthmap_to_absolute_camera_coordinates(d, K.numpy(), pose)
+    xb, mb = ref.depthmap_to_absolute_camera_coordinates(d, K.numpy(), pose)
+    assert np.allclose(xa, xb, atol=1e-6) and np.array_equal(ma, mb)
