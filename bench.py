@@ -210,6 +210,35 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` (profiles/r01_prof_kernels_v12.raw.csv),
+# for the shape that takes the largest share of each kernel class in the step
+NCU_TRAFFIC = {
+    'gemm_tcgen05_2cta_bn256': dict(bytes=109.1e6 + 353.4e6, shape='M=49152 N=4096 K=1024 bias+GELU (encoder fc1)',
+                                    algorithmic_bytes=(49152 * 1024 + 4096 * 1024 + 49152 * 4096) * 2),
+}
+
+
+def build_roofline(prof, pk, value, world):
+    """`roofline` object of the JSON line: the dominant kernel class of the instrumented step (CUDA events around every
+    launch) against the measured bf16 peak for a kernel timed inside a long step, plus the whole-step figure."""
+    tot_ms = sum(v['ms'] for v in prof.values()) or 1.0
+    name, dom = max(prof.items(), key=lambda kv: kv[1]['ms'])
+    dom_tflops = dom['flops'] / dom['ms'] / 1e9 if dom['flops'] and dom['ms'] else 0.0
+    alg_tflops = value * GFLOP_PER_PAIR / 1e3
+    traffic = NCU_TRAFFIC.get(name)
+    return dict(bound='tensor', kernel=name, achieved=dom_tflops, peak=pk['tf_sustained'], unit='TFLOP/s',
+                frac=dom_tflops / pk['tf_sustained'], traffic=traffic['bytes'] if traffic else None,
+                traffic_note=(f"{traffic['shape']}; algorithmic {traffic['algorithmic_bytes'] / 1e6:.1f} MB; "
+                              'profiles/r01_prof_kernels_v12.raw.csv') if traffic else None,
+                what='dominant kernel class of the step: algorithmic FLOP of its launches / their CUDA-event time, vs the measured '
+                     'cuBLAS bf16 peak sustained inside a long step (burst peak: frac_of_burst_peak)',
+                peak_source=pk['source'], launches=dom['count'], share_of_step=dom['ms'] / tot_ms,
+                frac_of_burst_peak=dom_tflops / pk['tf_burst'],
+                whole_step=dict(achieved=alg_tflops, peak=pk['tf_sustained'] * world, unit='TFLOP/s',
+                                frac=alg_tflops / (pk['tf_sustained'] * world),
+                                what='pairs/s x 1856.8 GFLOP/pair (SURVEY §8d) vs measured cuBLAS bf16 sustained peak'))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -306,8 +335,6 @@ def main():
         kern[k] = dict(launches=v['count'], ms=round(v['ms'], 3), share=round(v['ms'] / tot_ms, 4),
                        tflops=round(v['flops'] / v['ms'] / 1e9, 1) if v['flops'] and v['ms'] else None,
                        gbs=round(v['bytes'] / v['ms'] / 1e6, 1) if v['bytes'] and v['ms'] else None)
-    dom = max(prof.items(), key=lambda kv: kv[1]['ms'])
-    dom_tflops = dom[1]['flops'] / dom[1]['ms'] / 1e9 if dom[1]['flops'] else 0.0
 
     # ---- e2e through the public API: pinned host pairs -> inference() -> CPU dict ----
     e2e = None
@@ -335,8 +362,6 @@ def main():
             dist.destroy_process_group()
         return
     clocks = clk.summary()
-    alg_tflops = value * GFLOP_PER_PAIR / 1e3
-    peak = pk['tf_sustained'] * world
     line = dict(metric=METRIC, value=value, unit='image-pairs/s', n_gpus=world, steps=args.steps, warmup=W_,
                 ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16',
                 data='synthetic',
@@ -347,11 +372,7 @@ def main():
                             l2='activations per step (>5 GB) exceed the 126 MB L2; no explicit flush needed',
                             parallelism=f'dp{world}'),
                 clocks=clocks, e2e=e2e, gpu_launches=int(launches),
-                roofline=dict(bound='tensor', achieved=alg_tflops, peak=peak, unit='TFLOP/s', frac=alg_tflops / peak, traffic=None,
-                              what='whole step: pairs/s x 1856.8 GFLOP/pair (SURVEY §8d) vs measured cuBLAS bf16 sustained peak',
-                              peak_source=pk['source'],
-                              dominant_kernel=dict(name=dom[0], tflops=dom_tflops, frac_of_burst_peak=dom_tflops / pk['tf_burst'],
-                                                   share_of_step=dom[1]['ms'] / tot_ms)),
+                roofline=build_roofline(prof, pk, value, world),
                 kernels=kern)
     if world == 1 and not args.skip_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline_forward(1)

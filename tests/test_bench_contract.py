@@ -32,3 +32,26 @@ def test_reference_arm_other_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2', '--steps', '1',
                         '--warmup', '0'], capture_output=True, text=True, env=env, cwd=ROOT, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ''
+
+
+def test_build_roofline_on_a_recorded_breakdown():
+    """The `roofline` object is assembled by a pure function: feed it the per-kernel breakdown of a recorded run."""
+    sys.path.insert(0, ROOT)
+    import bench
+    rec = json.loads(open(os.path.join(ROOT, 'profiles', 'r01_bench_v13.json')).read().strip().splitlines()[-1])
+    prof = {k: dict(count=v['launches'], ms=v['ms'], flops=(v['tflops'] or 0.0) * v['ms'] * 1e9, bytes=(v['gbs'] or 0.0) * v['ms'] * 1e6)
+            for k, v in rec['kernels'].items()}
+    pk = dict(hbm=6556.2, tf_burst=1683.2, tf_sustained=1439.4, source='test')
+    for world in (1, 8):
+        r = bench.build_roofline(prof, pk, rec['value'] * world, world)
+        json.dumps(r)                                     # serialisable
+        assert r['bound'] == 'tensor' and r['unit'] == 'TFLOP/s' and r['kernel'] == 'gemm_tcgen05_2cta_bn256'
+        assert abs(r['frac'] - r['achieved'] / r['peak']) < 1e-12 and 0.5 < r['frac'] < 1.0
+        assert r['peak'] == pk['tf_sustained'] and 0 < r['frac_of_burst_peak'] < r['frac']
+        assert r['traffic'] and r['traffic'] < 1.2 * bench.NCU_TRAFFIC[r['kernel']]['algorithmic_bytes']
+        ws = r['whole_step']
+        assert abs(ws['achieved'] - rec['value'] * world * bench.GFLOP_PER_PAIR / 1e3) < 1e-6
+        assert abs(ws['frac'] - ws['achieved'] / (pk['tf_sustained'] * world)) < 1e-12
+    # a class the table has no capture for: traffic stays null
+    odd = bench.build_roofline({'some_kernel': dict(count=1, ms=1.0, flops=1e12, bytes=0.0)}, pk, 1.0, 1)
+    assert odd['traffic'] is None and odd['traffic_note'] is None and odd['achieved'] == 1000.0
