@@ -45,6 +45,31 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source='fallback (B200_PROFILING.md)')
 
 
+def host_threads(cap=64):
+    """Threads the CPU legs may use: min(affinity mask, cgroup cpu.max quota, cap).  torchrun exports OMP_NUM_THREADS=1 and
+    the affinity mask of a container is usually the whole host, so neither is a usable default: round 1's reference arm
+    ran 5x oversubscribed and was killed by the driver's limit."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        n = os.cpu_count() or 1
+    for path in ('/sys/fs/cgroup/cpu.max', '/sys/fs/cgroup/cpu/cpu.cfs_quota_us'):
+        try:
+            txt = open(path).read().split()
+            if path.endswith('cpu.max'):
+                if txt[0] != 'max':
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
+                    n = min(n, max(1, q // per))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return max(1, min(n, cap))
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
@@ -135,6 +160,7 @@ def cloud_opt_section(device, pk, steps_iters=300):
     ms = e0.elapsed_time(e1)
     by = eng.algorithmic_bytes_per_iter()
     gbs = by / (ms / steps_iters) / 1e6
+    tr = ncu_traffic().get('align_iter')
     # e2e through the public API: host dict in -> global_aligner -> compute_global_alignment -> float loss
     t0 = time.perf_counter()
     torch.manual_seed(0)
@@ -147,75 +173,132 @@ def cloud_opt_section(device, pk, steps_iters=300):
                                      '300 iters, lr 0.01 cosine, dist l1, conf log, init=None'),
                 ms_per_iter=ms / steps_iters, loss_first=float(losses[0]), loss_last=float(losses[-1]),
                 roofline=dict(bound='hbm', achieved=gbs, peak=pk['hbm'], unit='GB/s', frac=gbs / pk['hbm'],
-                              # dram__bytes_read+write per align_iter launch, ncu --set full on this exact workload
-                              # (profiles/r01_prof_align_v11.raw.csv): 195.15 + 10.55 MB
-                              traffic=205.7e6, traffic_source='profiles/r01_prof_align_v11.raw.csv',
+                              # dram__bytes_read+write per align_iter launch from the committed ncu --set full record
+                              traffic=tr['bytes'] if tr else None,
+                              traffic_source=f"{tr['capture']} @ {tr['commit']}" if tr else None,
                               algorithmic_bytes_per_iter=by, peak_source=pk['source']),
                 e2e=dict(value=steps_iters / t_api, unit='iters/s', includes='H2D of 28 pairs of predictions (pinned host memory, as returned by inference()), packing, 300 iters, loss readback',
                          final_loss=loss))
 
 
-def cpu_baseline_forward(n_pairs=1):
-    """Oracle port (CPU fp32 torch restatement of the reference forward) on the host cores."""
+def _oracle_forward_setup(threads):
     from dust3r_b200.config import vitl_512_dpt
     from dust3r_b200.utils.synth import synth_state_dict, synth_images
     from oracle.forward_oracle import forward_oracle
+    torch.set_num_threads(threads)
     cfg = vitl_512_dpt()
     sd = synth_state_dict(cfg, seed=0)
     imgs = synth_images(2, H, W, seed=3)
-    forward_oracle(sd, cfg, imgs[0]['img'][:, :, :64, :64], imgs[1]['img'][:, :, :64, :64])  # warm the thread pool
+    forward_oracle(sd, cfg, imgs[0]['img'][:, :, :64, :64], imgs[1]['img'][:, :, :64, :64])  # spin up the thread pool
+    return lambda: forward_oracle(sd, cfg, imgs[0]['img'], imgs[1]['img'])
+
+
+def cpu_baseline_forward(n_pairs=1):
+    """Oracle port (CPU fp32 torch restatement of the reference forward) on the host cores."""
+    threads = host_threads()
+    one_pair = _oracle_forward_setup(threads)
     t0 = time.perf_counter()
     for _ in range(n_pairs):
-        forward_oracle(sd, cfg, imgs[0]['img'], imgs[1]['img'])
+        one_pair()
     dt = time.perf_counter() - t0
-    return dict(value=n_pairs / dt, unit='image-pairs/s', cores=torch.get_num_threads(), kind='port',
-                sample=f'{n_pairs} pair(s) of 512x384, batch 1, oracle/forward_oracle.py (fp32 torch CPU restatement of the reference)')
+    return dict(value=n_pairs / dt, unit='image-pairs/s', cores=threads, kind='port',
+                sample=f'{n_pairs} pair(s) of 512x384, batch 1, oracle/forward_oracle.py (fp32 torch CPU restatement of the reference, '
+                       'bit-identical to it: tests/test_oracle.py)')
+
+
+def cpu_baseline_align(n_iters=3, budget_s=60.0):
+    """BASELINE.md §3, metric 2: the reference's alignment loop (autograd + torch.optim.Adam) on the host cores, as
+    restated by oracle/align_oracle.py ("reference cloud_opt + local roma restatement": `roma` is not installable
+    offline), on BASELINE configs[2] (8 views -> 28 pairs at 512x384), a few iterations after one warm-up iteration."""
+    from dust3r_b200.utils.synth import synth_pair_predictions
+    from oracle.align_oracle import AlignProblem, init_params, align_oracle
+    threads = host_threads()
+    torch.set_num_threads(threads)
+    n = 8
+    edges = [(i, j) for i in range(n) for j in range(i)]
+    out = synth_pair_predictions(n, edges, H, W, seed=0)
+    prob = AlignProblem.from_output(out)
+    P0 = init_params(prob, seed=0)
+    t0 = time.perf_counter()
+    align_oracle(prob, P0, niter=1)                      # warm-up (allocator, thread pool, autograd graph caches)
+    warm = time.perf_counter() - t0
+    n_iters = max(1, min(n_iters, int(budget_s / max(warm, 1e-3))))
+    t0 = time.perf_counter()
+    losses, _ = align_oracle(prob, P0, niter=n_iters)
+    dt = time.perf_counter() - t0
+    return dict(value=n_iters / dt, unit='iters/s', cores=threads, kind='port', s_per_iter=dt / n_iters,
+                sample=f'{n_iters} iterations (after 1 warm-up) of PointCloudOptimizer on 8 views / 28 pairs at 512x384, '
+                       'oracle/align_oracle.py = reference cloud_opt loop + local roma restatement', loss_first=float(losses[0]))
+
+
+REF_WARMUP_BUDGET_S = 60.0
+REF_TIMED_BUDGET_S = 170.0
 
 
 def run_reference_arm(args):
     """Reference arm: the reference's own CPU implementation of the path.  /root/reference does not exist on
     the GPU box and the reference has no compiled component for this path, so this times the oracle port
-    (validated bit-for-bit against the live reference in tests/test_oracle.py) on all host cores."""
+    (validated bit-for-bit against the live reference in tests/test_oracle.py) on the host cores this process
+    may really use (host_threads()).  One step = a bounded sample (1 pair, batch 1) of the 32-pair workload.
+    The whole run is bounded by wall clock: warm-up stops after REF_WARMUP_BUDGET_S, the timed loop stops
+    (and the line is still printed, with `steps` = the steps completed) once REF_TIMED_BUDGET_S are used."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    from dust3r_b200.config import vitl_512_dpt
-    from dust3r_b200.utils.synth import synth_state_dict, synth_images
-    from oracle.forward_oracle import forward_oracle
-    try:                                   # torchrun exports OMP_NUM_THREADS=1: take every host core this process may use
-        torch.set_num_threads(len(os.sched_getaffinity(0)))
-    except (AttributeError, RuntimeError):
-        torch.set_num_threads(os.cpu_count() or 1)
-    cfg = vitl_512_dpt()
-    sd = synth_state_dict(cfg, seed=0)
-    imgs = synth_images(2, H, W, seed=3)
+    threads = host_threads()
+    one_pair = _oracle_forward_setup(threads)
     sample_pairs = 1
-    for _ in range(max(args.warmup, 1) if args.warmup else 0):
-        forward_oracle(sd, cfg, imgs[0]['img'], imgs[1]['img'])
+    t_w = time.perf_counter()
+    done_w = 0
+    for _ in range(args.warmup):
+        one_pair()
+        done_w += 1
+        if time.perf_counter() - t_w > REF_WARMUP_BUDGET_S:
+            break
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    done = 0
+    last = 0.0
+    while done < args.steps:
+        ts = time.perf_counter()
         for _ in range(sample_pairs):
-            forward_oracle(sd, cfg, imgs[0]['img'], imgs[1]['img'])
+            one_pair()
+        done += 1
+        last = time.perf_counter() - ts
+        if done < args.steps and (time.perf_counter() - t0) + last > REF_TIMED_BUDGET_S:
+            break
     dt = time.perf_counter() - t0
-    val = args.steps * sample_pairs / dt
-    cores = torch.get_num_threads()
-    line = dict(impl='reference', metric=METRIC, value=val, unit='image-pairs/s', n_gpus=args.gpus, steps=args.steps,
-                warmup=args.warmup, ms_per_step=dt / args.steps * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None,
+    val = done * sample_pairs / dt
+    line = dict(impl='reference', metric=METRIC, value=val, unit='image-pairs/s', n_gpus=args.gpus, steps=done,
+                warmup=done_w, steps_requested=args.steps, warmup_requested=args.warmup,
+                ms_per_step=dt / done * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='f32', data='synthetic',
-                config=dict(workload='32 synthetic 512x384 pairs, ViTLarge_BaseDecoder_512_dpt forward (bounded sample: '
-                                     f'{sample_pairs} pair per step)', device='cpu'),
-                cpu_baseline=dict(value=val, unit='image-pairs/s', cores=cores, kind='port',
-                                  sample=f'{sample_pairs} pair per step x {args.steps} steps, batch 1'),
+                config=dict(workload=f'{PAIRS_PER_GPU} synthetic 512x384 pairs per GPU per step, ViTLarge_BaseDecoder_512_dpt forward only, '
+                                     f'not symmetrised (CPU arm: bounded sample of {sample_pairs} pair per step, batch 1)',
+                            weights='random init (synthetic, seed 0)', device='cpu', threads=threads,
+                            wall_bound_s=REF_WARMUP_BUDGET_S + REF_TIMED_BUDGET_S),
+                cpu_baseline=dict(value=val, unit='image-pairs/s', cores=threads, kind='port',
+                                  sample=f'{sample_pairs} pair per step x {done} steps, batch 1, oracle/forward_oracle.py'),
                 e2e=dict(value=val, unit='image-pairs/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    if not args.skip_cloud_opt:
+        try:
+            cb = cpu_baseline_align(n_iters=3, budget_s=40.0)
+            line['cloud_opt'] = dict(impl='reference', metric='cloud_opt iters/sec', value=cb['value'], unit='iters/s',
+                                     cpu_baseline=cb)
+        except Exception as ex:   # the forward line must be printed whatever happens to the extra leg
+            line['cloud_opt'] = dict(impl='reference', unavailable=f'{type(ex).__name__}: {ex}')
     print(json.dumps(line), flush=True)
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` (profiles/r01_prof_kernels_v12.raw.csv),
-# for the shape that takes the largest share of each kernel class in the step
-NCU_TRAFFIC = {
-    'gemm_tcgen05_2cta_bn256': dict(bytes=109.1e6 + 353.4e6, shape='M=49152 N=4096 K=1024 bias+GELU (encoder fc1)',
-                                    algorithmic_bytes=(49152 * 1024 + 4096 * 1024 + 49152 * 4096) * 2),
-}
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels, as recorded from `ncu --set full`
+    captures in profiles/ncu_traffic.json (each entry names its capture file and the commit it was taken at).  The bench
+    cannot run under ncu, so these are read from the committed record rather than measured in the timed run; an entry
+    that is missing yields traffic = null."""
+    path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    try:
+        return json.load(open(path))
+    except (OSError, ValueError):
+        return {}
 
 
 def build_roofline(prof, pk, value, world):
@@ -225,11 +308,11 @@ def build_roofline(prof, pk, value, world):
     name, dom = max(prof.items(), key=lambda kv: kv[1]['ms'])
     dom_tflops = dom['flops'] / dom['ms'] / 1e9 if dom['flops'] and dom['ms'] else 0.0
     alg_tflops = value * GFLOP_PER_PAIR / 1e3
-    traffic = NCU_TRAFFIC.get(name)
+    traffic = ncu_traffic().get(name)
     return dict(bound='tensor', kernel=name, achieved=dom_tflops, peak=pk['tf_sustained'], unit='TFLOP/s',
                 frac=dom_tflops / pk['tf_sustained'], traffic=traffic['bytes'] if traffic else None,
                 traffic_note=(f"{traffic['shape']}; algorithmic {traffic['algorithmic_bytes'] / 1e6:.1f} MB; "
-                              'profiles/r01_prof_kernels_v12.raw.csv') if traffic else None,
+                              f"{traffic['capture']} @ {traffic['commit']}") if traffic else None,
                 what='dominant kernel class of the step: algorithmic FLOP of its launches / their CUDA-event time, vs the measured '
                      'cuBLAS bf16 peak sustained inside a long step (burst peak: frac_of_burst_peak)',
                 peak_source=pk['source'], launches=dom['count'], share_of_step=dom['ms'] / tot_ms,
@@ -380,6 +463,8 @@ def main():
         del packed, net, imgs
         torch.cuda.empty_cache()
         line['cloud_opt'] = cloud_opt_section(device, pk)
+        if not args.skip_cpu_baseline:
+            line['cloud_opt']['cpu_baseline'] = cpu_baseline_align(n_iters=5, budget_s=30.0)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

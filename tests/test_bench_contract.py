@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_reference_arm_json_line():
     env = dict(os.environ, OMP_NUM_THREADS='1')     # torchrun exports this; the arm must still use every core
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '1', '--steps', '1',
-                        '--warmup', '0'], capture_output=True, text=True, env=env, cwd=ROOT, timeout=550)
+                        '--warmup', '0', '--skip-cloud-opt'], capture_output=True, text=True, env=env, cwd=ROOT, timeout=550)
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line['impl'] == 'reference' and line['higher_is_better'] is True and line['n_gpus'] == 1
@@ -25,6 +25,14 @@ def test_reference_arm_json_line():
     assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
     if (os.cpu_count() or 1) > 1:
         assert line['cpu_baseline']['cores'] > 1, 'reference arm must not stay on the single thread torchrun grants'
+
+
+def test_host_threads_respects_cgroup_quota_and_cap():
+    sys.path.insert(0, ROOT)
+    import bench
+    n = bench.host_threads()
+    assert 1 <= n <= 64 and n <= len(os.sched_getaffinity(0))
+    assert bench.host_threads(cap=2) <= 2
 
 
 def test_reference_arm_other_ranks_exit_quietly():
@@ -48,7 +56,7 @@ def test_build_roofline_on_a_recorded_breakdown():
         assert r['bound'] == 'tensor' and r['unit'] == 'TFLOP/s' and r['kernel'] == 'gemm_tcgen05_2cta_bn256'
         assert abs(r['frac'] - r['achieved'] / r['peak']) < 1e-12 and 0.5 < r['frac'] < 1.0
         assert r['peak'] == pk['tf_sustained'] and 0 < r['frac_of_burst_peak'] < r['frac']
-        assert r['traffic'] and r['traffic'] < 1.2 * bench.NCU_TRAFFIC[r['kernel']]['algorithmic_bytes']
+        assert r['traffic'] and r['traffic'] < 1.2 * bench.ncu_traffic()[r['kernel']]['algorithmic_bytes']
         ws = r['whole_step']
         assert abs(ws['achieved'] - rec['value'] * world * bench.GFLOP_PER_PAIR / 1e3) < 1e-6
         assert abs(ws['frac'] - ws['achieved'] / (pk['tf_sustained'] * world)) < 1e-12
