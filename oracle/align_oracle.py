@@ -4,7 +4,8 @@ legs may import this file.
 
 Parity status: pinned against the reference's own code executed here, with one caveat: the reference
 needs `roma`, which is absent, so the pinning runs are "reference cloud_opt + local roma restatement"
-(oracle/roma_stub).  tests/test_oracle_vs_reference.py re-checks it whenever /root/reference is mounted;
+(oracle/roma_stub; the stub's three entry points are themselves pinned against scipy's Rotation / weighted Kabsch
+and a float64 closed-form Umeyama in tests/test_roma_stub.py).  tests/test_oracle_vs_reference.py re-checks it whenever /root/reference is mounted;
 tests/golden/align_*.npz store the reference's loss trajectories and final parameters.
 
 Restates (autograd does the backward, torch.optim.Adam the update, exactly as the reference):

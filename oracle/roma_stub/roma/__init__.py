@@ -8,7 +8,9 @@ Restated from roma's public documentation (quaternions are XYZW, scalar last):
   RigidUnitQuat(q, t).normalize().to_homogeneous()  -> base_opt.py:154
   rotmat_to_unitquat(R)                             -> base_opt.py:169
   rigid_points_registration(x, y, weights, compute_scaling) -> init_im_poses.py:221,315
-This is not roma's code and is unverified against roma.
+This is not roma's code; roma itself cannot be run here.  The three entry points are pinned against independent
+implementations instead (tests/test_roma_stub.py): scipy.spatial.transform.Rotation for both quaternion maps (XYZW),
+scipy's weighted Kabsch and a float64 closed-form weighted Umeyama for the registration, plus an optimality check.
 """
 import torch
 
