@@ -33,6 +33,8 @@ class AlignDesc(C.Structure):
         ('logd', C.c_void_p), ('logd_m', C.c_void_p), ('logd_v', C.c_void_p),
         ('small', C.c_void_p), ('small_m', C.c_void_p), ('small_v', C.c_void_p), ('small_trainable', C.c_void_p),
         ('workspace', C.c_void_p), ('sched', C.c_void_p), ('loss_out', C.c_void_p), ('counters', C.c_void_p),
+        ('stream_kernel', C.c_int32), ('stream_grid', C.c_int32), ('stream_ppt', C.c_int32), ('stream_window', C.c_int32),
+        ('n_items', C.c_int32), ('reserved0', C.c_int32), ('items', C.c_void_p), ('warp_item_ptr', C.c_void_p),
     ]
 
 
@@ -65,6 +67,12 @@ def _declare(lib):
     lib.d3r_align_pts3d.argtypes = [C.POINTER(AlignDesc), vp, vp]
     lib.d3r_align_pack_obs.restype = C.c_int
     lib.d3r_align_pack_obs.argtypes = [vp, vp, vp, i64, i64, vp]
+    lib.d3r_align_pack_entries.restype = C.c_int
+    lib.d3r_align_pack_entries.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+    for name in ('d3r_sizeof_align_item', 'd3r_sizeof_pack_entry', 'd3r_align_stream_slots_per_item',
+                 'd3r_align_stream_warps_per_cta', 'd3r_align_stream_max_window'):
+        getattr(lib, name).restype = C.c_int
+        getattr(lib, name).argtypes = []
 
 
 def lib_available() -> bool:

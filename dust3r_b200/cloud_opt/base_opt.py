@@ -28,7 +28,7 @@ class BasePCOptimizer(nn.Module):
     # attributes shared (not copied) when one optimizer is built from another one
     _SCENE_ATTRS = ('edges', 'is_symmetrized', 'dist', 'n_imgs', 'pred_i', 'pred_j', 'imshapes', 'min_conf_thr', 'conf_thr',
                     'conf_i', 'conf_j', 'im_conf', 'base_scale', 'norm_pw_scale', 'POSE_DIM', 'pw_poses', 'pw_adaptors',
-                    'has_im_poses', 'rand_pose', 'imgs', 'verbose')
+                    'has_im_poses', 'rand_pose', 'imgs', 'verbose', 'conf_mode', 'conf_trf', 'pw_break', 'align_kernel')
 
     def __init__(self, *args, **kwargs):
         if len(args) == 1 and not kwargs:
@@ -42,13 +42,14 @@ class BasePCOptimizer(nn.Module):
     def _init_from_views(self, view1, view2, pred1, pred2,
                          dist='l1', conf='log', min_conf_thr=3, base_scale=0.5,
                          allow_pw_adaptors=False, pw_break=20, rand_pose=torch.randn,
-                         iterationsCount=None, verbose=True):
+                         iterationsCount=None, verbose=True, kernel='auto'):
         """Scene graph from the output of inference(): view*['idx'] give the image ids of every pair, pred1 / pred2 the
         two pointmaps (+ confidences) of every pair, both expressed in the first image's camera frame."""
         super().__init__()
         if dist not in ALL_DISTS:
             raise KeyError(dist)
         self.dist, self.verbose = dist, verbose
+        self.align_kernel = kernel       # extension: 'auto' | 'stream' | 'general' (which fused CUDA step runs the loop)
 
         # ---- graph
         for view in (view1, view2):
@@ -63,6 +64,11 @@ class BasePCOptimizer(nn.Module):
         def per_edge(stacked):
             return NoGradParamDict({key: stacked[e] for e, key in enumerate(self.str_edges)})
         pts_i, pts_j = pred1['pts3d'], pred2['pts3d_in_other_view']
+        # equal-size scenes arrive as 4 stacked tensors: remember them so that .to(device) moves 4 buffers (one H2D
+        # copy each, or none at all when inference(keep_on_device=True) / the all-gather left them in HBM) and the
+        # per-edge dictionaries stay views of them, instead of 4E separate parameter copies
+        stacks = (pts_i, pts_j, pred1['conf'], pred2['conf'])
+        self._obs_stacks = stacks if all(torch.is_tensor(t) for t in stacks) else None
         self.pred_i, self.pred_j = per_edge(pts_i), per_edge(pts_j)
         self.imshapes = get_imshapes(self.edges, pts_i, pts_j)
         self.min_conf_thr = min_conf_thr
@@ -114,9 +120,26 @@ class BasePCOptimizer(nn.Module):
         self._engine = None
         return super().load_state_dict(self.state_dict(trainable=False) | data)
 
+    _OBS_DICTS = ('pred_i', 'pred_j', 'conf_i', 'conf_j')
+
     def _apply(self, fn, *a, **kw):
         self._engine = None  # device / dtype moves invalidate the packed observation buffer
-        return super()._apply(fn, *a, **kw)
+        stacks = self.__dict__.get('_obs_stacks')
+        if stacks is None:
+            return super()._apply(fn, *a, **kw)
+        # move the 4 stacked observation tensors once and re-create the per-edge views on the result
+        held = {name: self._modules.pop(name) for name in self._OBS_DICTS}
+        try:
+            super()._apply(fn, *a, **kw)
+            moved = tuple(fn(t) for t in stacks)
+        except Exception:
+            self._modules.update(held)
+            raise
+        self._obs_stacks = moved
+        keys = self.str_edges
+        for name, stacked in zip(self._OBS_DICTS, moved):
+            self._modules[name] = NoGradParamDict({key: stacked[e] for e, key in enumerate(keys)})
+        return self
 
     def _check_edges(self):
         indices = sorted({i for edge in self.edges for i in edge})
@@ -229,10 +252,11 @@ class BasePCOptimizer(nn.Module):
         self._engine = AlignEngine(
             self.edges, self.imshapes,
             [self.pred_i[k] for k in keys], [self.pred_j[k] for k in keys],
-            [self.conf_trf(self.conf_i[k]) for k in keys], [self.conf_trf(self.conf_j[k]) for k in keys],
-            device=dev, dist=self.dist, variant=self._engine_variant(), pix_stride=self._engine_pix_stride(),
+            [self.conf_i[k] for k in keys], [self.conf_j[k] for k in keys],
+            device=dev, conf_mode=self.conf_mode, dist=self.dist, variant=self._engine_variant(), pix_stride=self._engine_pix_stride(),
             base_scale=self.base_scale, pw_break=self.pw_break,
-            focal_break=getattr(self, 'focal_break', getattr(self, 'focal_brake', 20)))
+            focal_break=getattr(self, 'focal_break', getattr(self, 'focal_brake', 20)),
+            kernel=getattr(self, 'align_kernel', 'auto'))
         return self._engine
 
     def _engine_push(self, eng):

@@ -21,12 +21,63 @@ from .. import _lib
 from .commons import cosine_schedule, linear_schedule
 
 
+_CONF_MODES = {'id': 0, 'none': 0, 'log': 1, 'sqrt': 2, 'm1': 3}
+
+PACK_ENTRY = np.dtype([('pts', np.uint64), ('conf', np.uint64), ('obs_off', np.int64), ('area', np.int32), ('coef', np.float32)])
+ITEM = np.dtype([('img', np.int32), ('slot0', np.int32), ('nslots', np.int32), ('npx', np.int32),
+                 ('e0', np.int32), ('deg', np.int32), ('W', np.int32), ('u0', np.int32),
+                 ('v0', np.int32), ('inv_w', np.float32), ('pix0', np.int64), ('obs0', np.int64),
+                 ('slab_units', np.int32), ('reserved', np.int32)])
+SLOT_PX = 64          # pixels per slot of the streaming layout (32 pixel pairs)
+
+
+def build_stream_items(imshapes, pix_off, ent_ptr, ent_obs_off, slots, ppt, warps_per_cta, max_ctas):
+    """Work items of the streaming kernel (csrc/align_stream.cu).  Every image's range of 64-pixel slots is cut into
+    items of <= ppt slots; the global slot sequence is split into one contiguous run per persistent warp, balanced by
+    cost = slots x (entries of the image + fixed per-pixel work).  Returns (items[ITEM], warp_item_ptr[int32], ctas)."""
+    n = len(imshapes)
+    areas = [h * w for h, w in imshapes]
+    deg = np.diff(ent_ptr).astype(np.int64)
+    slot_img = np.repeat(np.arange(n), slots)                      # image of every slot, global slot order
+    slot_idx = np.concatenate([np.arange(s) for s in slots])       # slot index inside its image
+    cost = (deg[slot_img] + 3).astype(np.float64)
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    total = len(slot_img)
+    n_warps = int(min(max_ctas * warps_per_cta, total))
+    grid = (n_warps + warps_per_cta - 1) // warps_per_cta
+    bounds = np.searchsorted(cum, cum[-1] * np.arange(n_warps + 1) / n_warps, side='left')
+    bounds = np.concatenate([np.minimum(bounds, total), np.full(grid * warps_per_cta - n_warps, total, dtype=bounds.dtype)])
+    bounds[0], bounds[n_warps:] = 0, total
+    items, warp_ptr = [], [0]
+    for w in range(grid * warps_per_cta):
+        s, b = int(bounds[w]), int(bounds[w + 1])
+        while s < b:
+            img = int(slot_img[s])
+            seg_end = min(b, s + (slots[img] - int(slot_idx[s])))   # stay inside the image
+            H, W = imshapes[img]
+            while s < seg_end:
+                ns = min(ppt, seg_end - s)
+                s0 = int(slot_idx[s])
+                p0 = s0 * SLOT_PX
+                items.append((img, s0, ns, min(ns * SLOT_PX, areas[img] - p0), int(ent_ptr[img]), int(deg[img]), W,
+                              p0 % W, p0 // W, np.float32(1.0 / W), int(pix_off[img]) + p0,
+                              (int(ent_obs_off[ent_ptr[img]]) + p0) if deg[img] > 0 else 0, slots[img] * SLOT_PX, 0))
+                s += ns
+        warp_ptr.append(len(items))
+    return np.array(items, dtype=ITEM), np.asarray(warp_ptr, dtype=np.int32), grid
+
+
 class AlignEngine:
+    """pred_i / pred_j: per-edge (H, W, 3) pointmaps; conf_i / conf_j: per-edge RAW confidences (H, W) -- the
+    confidence transform `conf_mode` (commons.py:73-80) is applied by the packing kernel.  Tensors already on
+    `device` (e.g. views of inference(keep_on_device=True) / all-gather output) are read in place; everything is
+    packed by ONE launch (d3r_align_pack_entries)."""
+
     def __init__(self, edges: Sequence[Tuple[int, int]], imshapes: Sequence[Tuple[int, int]],
                  pred_i: Sequence[torch.Tensor], pred_j: Sequence[torch.Tensor],
-                 weight_i: Sequence[torch.Tensor], weight_j: Sequence[torch.Tensor],
-                 device, dist='l1', variant='stacked', pix_stride=None,
-                 base_scale=0.5, pw_break=20.0, focal_break=20.0):
+                 conf_i: Sequence[torch.Tensor], conf_j: Sequence[torch.Tensor],
+                 device, conf_mode='log', dist='l1', variant='stacked', pix_stride=None,
+                 base_scale=0.5, pw_break=20.0, focal_break=20.0, kernel='auto'):
         self.device = _lib.require_cuda_device(device)
         self.lib = _lib.get_lib()
         self.edges = [(int(i), int(j)) for i, j in edges]
@@ -34,6 +85,8 @@ class AlignEngine:
         self.n, self.E = len(self.imshapes), len(self.edges)
         n, E = self.n, self.E
         assert dist in ('l1', 'l2')
+        if conf_mode not in _CONF_MODES:
+            raise ValueError(f'bad mode for {conf_mode=}')
         self.dist, self.variant = dist, variant
         self.base_scale, self.pw_break, self.focal_break = float(base_scale), float(pw_break), float(focal_break)
         areas = [h * w for h, w in self.imshapes]
@@ -44,6 +97,16 @@ class AlignEngine:
         pix_off = np.zeros(n + 1, dtype=np.int64)
         pix_off[1:] = np.cumsum(self.pix_stride)
         self.pix_off = pix_off
+        # streaming kernel (csrc/align_stream.cu): needs 16-byte aligned log-depth slices.  DUSt3R images are multiples
+        # of the 16-pixel patch, so this is the path real inputs take; odd shapes run the general kernel.
+        eligible = all(a % 4 == 0 for a in areas) and all(int(o) % 4 == 0 for o in pix_off)
+        if kernel == 'auto':
+            kernel = 'stream' if eligible else 'general'
+        if kernel == 'stream' and not eligible:
+            raise ValueError('the streaming alignment kernel needs H*W and the pixel stride of every image to be multiples of 4')
+        assert kernel in ('stream', 'general')
+        self.kernel = kernel
+        stream = kernel == 'stream'
         chunk = self._pick_chunk_px(areas)
         self.chunk_px = chunk
         nchunks = [(a + chunk - 1) // chunk for a in areas]
@@ -63,9 +126,19 @@ class AlignEngine:
         edge_ent = np.zeros((E, 2), dtype=np.int32)
         if variant == 'stacked':     # optimizer.py:59-60,198-199: sum / total_area per side
             tot = [sum(areas[i] for i, j in self.edges), sum(areas[j] for i, j in self.edges)]
+        slots = [(a + SLOT_PX - 1) // SLOT_PX for a in areas]
         k = 0
         off = 0
-        order = []
+        table = np.zeros(2 * E, dtype=PACK_ENTRY)
+        keep = []                     # device copies of host inputs stay alive until the pack launch has run
+        dev = self.device
+
+        def on_dev(t, width):
+            t = t.reshape(-1, width) if width > 1 else t.reshape(-1)
+            if t.device != dev or t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.to(dev, torch.float32).contiguous()
+                keep.append(t)
+            return t
         for img in range(n):
             for (e, side) in ent_lists[img]:
                 ent_edge[k] = e
@@ -75,11 +148,14 @@ class AlignEngine:
                 else:                # base_opt.py:262-270: mean over pixels, then / n_edges
                     ent_coef[k] = 1.0 / (areas[img] * E)
                 edge_ent[e, side] = k
-                order.append((e, side, off, areas[img]))
-                off += areas[img]
+                pts = on_dev((pred_i if side == 0 else pred_j)[e], 3)
+                cf = on_dev((conf_i if side == 0 else conf_j)[e], 1)
+                assert pts.shape[0] >= areas[img] and cf.shape[0] >= areas[img]
+                table[k] = (pts.data_ptr(), cf.data_ptr(), off, areas[img], ent_coef[k])
+                off += slots[img] * SLOT_PX if stream else areas[img]
                 k += 1
         self.total_obs = off
-        dev = self.device
+        self.obs_px = sum(areas[i] + areas[j] for i, j in self.edges)      # algorithmic observation count (no padding)
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
         self._img_hw = t(np.int32(self.imshapes))
         self._pix_off = t(pix_off)
@@ -93,15 +169,16 @@ class AlignEngine:
         self.n_chunks = int(chunk_ptr[-1])
         self.max_chunks = int(max(nchunks))
         self.max_deg = int(max(len(l) for l in ent_lists))
-        # observations
+        # observations: one launch for every entry, confidence transform and (streaming layout) loss coefficient fused
         self.obs = torch.empty((self.total_obs, 4), dtype=torch.float32, device=dev)
-        sp = _lib.stream_ptr()
-        for (e, side, o, area) in order:
-            pts = (pred_i if side == 0 else pred_j)[e]
-            w = (weight_i if side == 0 else weight_j)[e]
-            pts = pts.reshape(-1, 3)[:area].to(dev, torch.float32).contiguous()
-            w = w.reshape(-1)[:area].to(dev, torch.float32).contiguous()
-            _lib.check(self.lib.d3r_align_pack_obs(pts.data_ptr(), w.data_ptr(), self.obs.data_ptr(), o, area, sp))
+        table_dev = torch.from_numpy(table.view(np.uint8)).to(dev)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.d3r_align_pack_entries(table_dev.data_ptr(), 2 * E, int(max(areas)), _CONF_MODES[conf_mode],
+                                                       1 if stream else 0, self.obs.data_ptr(), self._stream()))
+        if keep:
+            torch.cuda.current_stream(dev).synchronize()     # the staged copies may be freed after this point
+        del keep, table_dev
+        self._build_items(ent_ptr, ent_obs_off, slots) if stream else self._no_items()
         nws = self.lib.d3r_align_workspace_floats(n, E, self.n_chunks, self.max_chunks)
         self.workspace = torch.zeros((nws,), dtype=torch.float32, device=dev)
         self.counters = torch.zeros((n + 2,), dtype=torch.int32, device=dev)
@@ -116,6 +193,34 @@ class AlignEngine:
         self.loss_out = torch.zeros((1,), dtype=torch.float32, device=dev)
         self.norm_pw_scale = True
         self.tied_focal = True
+
+    def _stream(self):
+        """cudaStream_t of the engine's device (never the current device's: global_aligner(out, 'cuda:1') must work
+        while cuda:0 is current)."""
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _call(self, fn, *args):
+        with torch.cuda.device(self.device):
+            _lib.check(fn(*args, self._stream()))
+
+    def _no_items(self):
+        self.stream_grid = self.stream_ppt = self.stream_window = self.n_items = 0
+        self._items = self._warp_item_ptr = None
+
+    def _build_items(self, ent_ptr, ent_obs_off, slots):
+        lib = self.lib
+        ppt = int(lib.d3r_align_stream_slots_per_item())
+        wpc = int(lib.d3r_align_stream_warps_per_cta())
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        arr, warp_ptr, grid = build_stream_items(self.imshapes, self.pix_off, ent_ptr, ent_obs_off, slots, ppt, wpc, 2 * sms)
+        assert arr.dtype.itemsize == 64 == lib.d3r_sizeof_align_item()
+        dev = self.device
+        self._items = torch.from_numpy(arr.view(np.uint8)).to(dev)
+        self._warp_item_ptr = torch.from_numpy(warp_ptr).to(dev)
+        self.n_items = len(arr)
+        self.stream_grid, self.stream_ppt = grid, ppt
+        deg_max = int(np.diff(ent_ptr).max())
+        self.stream_window = int(min(max(deg_max, 1), lib.d3r_align_stream_max_window()))
 
     def _pick_chunk_px(self, areas):
         """Pixels per CTA: the largest size <= the kernel's maximum for which the grid is (close to) a whole
@@ -136,7 +241,7 @@ class AlignEngine:
     # ------------------------------------------------------------------ parameters
     def algorithmic_bytes_per_iter(self):
         """32*E*P (observations read once) + 24*n*P (log-depth + 2 moments r/w)."""
-        return 16 * self.total_obs + 24 * sum(self.areas)
+        return 16 * self.obs_px + 24 * sum(self.areas)
 
     def _offsets(self):
         n, E = self.n, self.E
@@ -227,11 +332,15 @@ class AlignEngine:
         d.sched = self.sched.data_ptr()
         d.loss_out = self.loss_out.data_ptr()
         d.counters = self.counters.data_ptr()
+        d.stream_kernel = 1 if self.kernel == 'stream' else 0
+        d.stream_grid, d.stream_ppt, d.stream_window, d.n_items = self.stream_grid, self.stream_ppt, self.stream_window, self.n_items
+        if self.kernel == 'stream':
+            d.items, d.warp_item_ptr = self._items.data_ptr(), self._warp_item_ptr.data_ptr()
         return d
 
     def prepare(self):
         d = self._desc()
-        _lib.check(self.lib.d3r_align_prepare(C.byref(d), _lib.stream_ptr()))
+        self._call(self.lib.d3r_align_prepare, C.byref(d))
         self._prepared = True
 
     @staticmethod
@@ -264,14 +373,14 @@ class AlignEngine:
         if not getattr(self, '_prepared', False):
             self.prepare()
         d = self._desc()
-        _lib.check(self.lib.d3r_align_run(C.byref(d), 0, niter, _lib.stream_ptr()))
+        self._call(self.lib.d3r_align_run, C.byref(d), 0, niter)
         return self.loss_out
 
     def check_overflow(self):
         """Raises if a fixed-point accumulator left its range (host sync)."""
         flag = C.c_int32(0)
         d = self._desc()
-        _lib.check(self.lib.d3r_align_overflow_flag(C.byref(d), C.byref(flag), _lib.stream_ptr()))
+        self._call(self.lib.d3r_align_overflow_flag, C.byref(d), C.byref(flag))
         if flag.value:
             raise _lib.D3RError('alignment: a gradient partial sum exceeded the fixed-point accumulator range (|x| >= 2^18); '
                                 'rescale the scene (pointmaps are expected in metric-like units)')
@@ -282,7 +391,7 @@ class AlignEngine:
         self.loss_out = torch.zeros((1,), dtype=torch.float32, device=self.device)
         self.prepare()
         d = self._desc(eval_only=True)
-        _lib.check(self.lib.d3r_align_run(C.byref(d), 0, 1, _lib.stream_ptr()))
+        self._call(self.lib.d3r_align_run, C.byref(d), 0, 1)
         return self.loss_out[0]
 
     def pts3d(self):
@@ -290,5 +399,5 @@ class AlignEngine:
         self.prepare()
         out = torch.zeros((int(self.pix_off[-1]), 3), dtype=torch.float32, device=self.device)
         d = self._desc()
-        _lib.check(self.lib.d3r_align_pts3d(C.byref(d), out.data_ptr(), _lib.stream_ptr()))
+        self._call(self.lib.d3r_align_pts3d, C.byref(d), out.data_ptr())
         return out

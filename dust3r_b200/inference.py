@@ -134,7 +134,7 @@ def inference(pairs, model, device, batch_size=8, verbose=True, keep_on_device=F
     proto = [vs[0]['img'] for vs in views]
     # pinned staging = the collated 'img' of the returned views; device copies of the whole pair list (a few MB / pair)
     img_pin = [torch.empty((rows[k],) + tuple(proto[k].shape[1:]), dtype=proto[k].dtype, pin_memory=True) for k in range(2)]
-    img_dev = [torch.empty(img_pin[k].shape, dtype=img_pin[k].dtype, device=dev) for k in range(2)]
+    img_dev = None    # device copies of both views: only the non-deduplicated path needs them (allocated there)
     meta_all = [{key: collate_with_cat([v[key] for v in vs]) for key in vs[0] if key != 'img'} for vs in views]
     _mark('alloc+meta')
     outs = None
@@ -193,6 +193,8 @@ def inference(pairs, model, device, batch_size=8, verbose=True, keep_on_device=F
             _mark('h2d+meta')
             pred1, pred2 = model.forward_indexed(sel, [loc[g] for g in g1], [loc[g] for g in g2])
         else:
+            if img_dev is None:
+                img_dev = [torch.empty(img_pin[k].shape, dtype=img_pin[k].dtype, device=dev) for k in range(2)]
             with torch.cuda.stream(up):
                 for k in range(2):
                     if direct:

@@ -116,10 +116,41 @@ typedef struct d3r_align_desc {
   float* loss_out;              /* [niter_total] loss of every iteration                    */
   int32_t* counters;            /* [n + 2] zero-initialised by the caller once              */
   /* `workspace` must be zero-initialised by the caller once as well (accumulators live there).  */
+
+  /* ---- streaming kernel (csrc/align_stream.cu), used when every image has P % 4 == 0 and a pixel stride
+   * that is a multiple of 4 (always true for DUSt3R inputs: H, W are multiples of the 16-pixel patch).
+   * stream_kernel = 1 selects it; obs then holds the slot-interleaved layout written by
+   * d3r_align_pack_obs_stream (same 16 bytes per observation):
+   *   per entry: slots of 64 pixels = [32 x (xA,xB,yA,yB)] [32 x (zA,zB,wA,wB)] for the 32 pixel pairs
+   *   (A,B) = (2j, 2j+1) of the slot, the loss coefficient folded into w; every image's slab is padded to
+   *   whole slots with w = 0.
+   * The pixel range of every image is cut into work items of <= ppt slots; persistent warp w owns items
+   * [warp_item_ptr[w], warp_item_ptr[w+1]).                                                           */
+  int32_t stream_kernel;
+  int32_t stream_grid;          /* CTAs of the persistent grid                                       */
+  int32_t stream_ppt;           /* slots (64 pixels) per work item, 2..4                              */
+  int32_t stream_window;        /* entries whose partial sums a warp keeps in shared memory            */
+  int32_t n_items;
+  int32_t reserved0;
+  const void* items;            /* [n_items] d3r_align_item                                            */
+  const int32_t* warp_item_ptr; /* [stream_grid * 8 + 1]                                               */
 } d3r_align_desc;
 
-/* sizeof(d3r_align_desc) as compiled into the library (binding self-check). */
+/* One work item of the streaming kernel: `nslots` consecutive 64-pixel slots of image `img`. */
+typedef struct d3r_align_item {
+  int32_t img, slot0, nslots, npx;     /* npx: valid pixels of the item (multiple of 4)               */
+  int32_t e0, deg, W, u0;              /* first entry / number of entries of the image; width; column of the first pixel */
+  int32_t v0;                          /* row of the first pixel                                      */
+  float inv_w;                         /* 1 / W                                                       */
+  int64_t pix0;                        /* img_pix_off[img] + 64 * slot0: index into logd / adam moments */
+  int64_t obs0;                        /* 16-byte units: first entry's slab of the image + 64 * slot0   */
+  int32_t slab_units;                  /* 16-byte units per entry slab of this image (64 * slots)      */
+  int32_t reserved;
+} d3r_align_item;
+
+/* sizeof(d3r_align_desc) / sizeof(d3r_align_item) as compiled into the library (binding self-check). */
 int d3r_sizeof_align_desc(void);
+int d3r_sizeof_align_item(void);
 /* Maximum pixels one CTA of the alignment kernel can take (compile-time constant of the library). */
 int d3r_align_chunk_pixels(void);
 /* Number of floats of `workspace` needed for a problem of this size. */
@@ -141,6 +172,31 @@ int d3r_align_set_debug(void* dev_buf);
 /* Packs pred (P,3) + weight (P) rows into the float4 observation layout. */
 int d3r_align_pack_obs(const float* pts_dev, const float* weight_dev, void* obs_dev, int64_t obs_off,
                        int64_t n_pix, void* stream);
+
+/* Packs EVERY entry's observations in one launch, straight from the (device-resident) output of the forward:
+ * replaces the ParameterStack copies + conf_trf of optimizer.py:50-57 / base_opt.py:72-75.  `table` (dev) has one
+ * row per entry; the confidence transform (commons.py:73-80: D3R_CONF_ID / LOG / SQRT / M1) is applied on the fly.
+ * stream_layout = 0: plain float4 (x, y, z, w) rows; 1: the slot-interleaved layout of the streaming kernel, the
+ * loss coefficient folded into w and slabs padded to whole 64-pixel slots with zeros. */
+#define D3R_CONF_ID 0
+#define D3R_CONF_LOG 1
+#define D3R_CONF_SQRT 2
+#define D3R_CONF_M1 3
+typedef struct d3r_pack_entry {
+  const float* pts;        /* dev: (area, 3) pointmap of the entry                                       */
+  const float* conf;       /* dev: (area) raw confidence                                                  */
+  int64_t obs_off;         /* float4 units: where the entry's slab starts in obs                          */
+  int32_t area;            /* pixels of the entry                                                         */
+  float coef;              /* loss coefficient of the entry (folded into w when stream_layout = 1)        */
+} d3r_pack_entry;
+int d3r_sizeof_pack_entry(void);
+/* Compile-time constants of the streaming kernel the host needs to build the work-item table: slots (64 pixels) per
+ * item, persistent warps per CTA, and the largest entry window for which two CTAs still fit one SM. */
+int d3r_align_stream_slots_per_item(void);
+int d3r_align_stream_warps_per_cta(void);
+int d3r_align_stream_max_window(void);
+int d3r_align_pack_entries(const d3r_pack_entry* table_dev, int32_t n_entries, int32_t max_area, int32_t conf_mode,
+                           int32_t stream_layout, void* obs_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Path 1 building blocks — exported so the parity tests can exercise each kernel in isolation.

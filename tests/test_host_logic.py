@@ -149,3 +149,42 @@ def test_geometry_helpers_match_live_reference():
     xa, ma = mine.depthmap_to_absolute_camera_coordinates(d, K.numpy(), pose)
     xb, mb = ref.depthmap_to_absolute_camera_coordinates(d, K.numpy(), pose)
     assert np.allclose(xa, xb, atol=1e-6) and np.array_equal(ma, mb)
+
+
+def test_stream_work_items_cover_every_slot_once_and_balance():
+    """Host-side decomposition of the streaming alignment kernel: every 64-pixel slot of every image belongs to exactly
+    one work item, items never cross an image, per-warp lists are contiguous and cost-balanced to within one slot."""
+    import numpy as np
+    from dust3r_b200.cloud_opt.engine import build_stream_items, SLOT_PX
+    rng = np.random.default_rng(0)
+    for imshapes, deg in (([(384, 512)] * 8, [7] * 8), ([(24, 32), (20, 36), (14, 44)], [2, 3, 3]), ([(128, 160)] * 50, [49] * 50),
+                          ([(8, 16)] * 5, [4, 1, 9, 2, 6])):
+        n = len(imshapes)
+        areas = [h * w for h, w in imshapes]
+        slots = [(a + SLOT_PX - 1) // SLOT_PX for a in areas]
+        pix_off = np.concatenate([[0], np.cumsum(areas)]).astype(np.int64)
+        ent_ptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+        ent_obs_off = np.concatenate([[0], np.cumsum(np.repeat(np.array(slots) * SLOT_PX, deg))])[:-1].astype(np.int64)
+        items, wptr, grid = build_stream_items(imshapes, pix_off, ent_ptr, ent_obs_off, slots, 3, 8, 296)
+        assert len(wptr) == grid * 8 + 1 and wptr[0] == 0 and wptr[-1] == len(items) and np.all(np.diff(wptr) >= 0)
+        seen = [np.zeros(s, dtype=int) for s in slots]
+        for it in items:
+            assert 1 <= it['nslots'] <= 3 and it['slot0'] + it['nslots'] <= slots[it['img']]
+            seen[it['img']][it['slot0']:it['slot0'] + it['nslots']] += 1
+            p0 = it['slot0'] * SLOT_PX
+            H, W = imshapes[it['img']]
+            assert it['npx'] == min(it['nslots'] * SLOT_PX, areas[it['img']] - p0) and it['npx'] % 4 == 0
+            assert it['v0'] * W + it['u0'] == p0 and it['pix0'] == pix_off[it['img']] + p0
+            assert it['obs0'] == ent_obs_off[ent_ptr[it['img']]] + p0 and it['slab_units'] == slots[it['img']] * SLOT_PX
+            assert it['e0'] == ent_ptr[it['img']] and it['deg'] == deg[it['img']]
+        assert all(np.all(s == 1) for s in seen)
+        # items of one warp are consecutive slots of the global sequence
+        glob = np.concatenate([[0], np.cumsum(slots)])
+        cost = []
+        for w in range(grid * 8):
+            its = items[wptr[w]:wptr[w + 1]]
+            pos = [glob[i['img']] + i['slot0'] for i in its]
+            assert all(pos[k + 1] == pos[k] + its[k]['nslots'] for k in range(len(its) - 1))
+            cost.append(sum(int(i['nslots']) * (int(i['deg']) + 3) for i in its))
+        busy = [c for c in cost if c > 0]
+        assert max(busy) - min(busy) <= 2 * (max(deg) + 3), (max(busy), min(busy))
