@@ -70,9 +70,15 @@ __device__ __forceinline__ void sb_bulk(uint32_t dst, const void* src, uint32_t 
 }
 
 struct ProdState {          // per warp, touched by lane 0 only
-  int item, item_end, phase;
-  int slot;                 // ring slot the next stage goes to
-  d3r_align_item hdr;       // header of the item being produced
+  int item, item_end;
+  int phase, deg;           // stage to issue next: 0 = L, 1..deg = E_{phase-1}, deg+1 = MV
+  int slot;                 // ring slot it goes to
+  uint32_t px_bytes, pay_bytes;
+  int slab_units;           // 16-byte units between the slabs of consecutive entries
+  const float* row;         // transform row of the next entry
+  const uint4* obs;         // observations of the next entry for this item's pixels
+  const float* irow;        // image transform row
+  int64_t pix0;             // first pixel of the item in logd / logd_m / logd_v
 };
 
 // Sums NV per-lane values over the warp through a transpose in shared memory.  Lanes 2v and 2v+1 return the total of
@@ -93,7 +99,7 @@ __device__ __forceinline__ float warp_transpose_sum(const float (&a)[NV], float*
   return t;
 }
 
-// Issues the next stage of this warp's sequence into ring slot gp % NST (lane 0 only).
+// Issues the next stage of this warp's sequence into its ring slot (lane 0 only).
 template <int PPT, int NST>
 __device__ __forceinline__ void produce_next(const d3r_align_desc& D, const Workspace& ws, ProdState* ps, uint8_t* ring,
                                              uint64_t* full) {
@@ -103,38 +109,169 @@ __device__ __forceinline__ void produce_next(const d3r_align_desc& D, const Work
   const int s = ps->slot;
   const uint32_t dst = s_u32(ring + s * kStage);
   const uint32_t bar = s_u32(&full[s]);
-  int phase = ps->phase;
-  const d3r_align_item* gh = reinterpret_cast<const d3r_align_item*>(D.items) + item;
-  if (phase == 0) ps->hdr = *gh;     // cache the item header for the deg + 2 stages of this item
-  const d3r_align_item& h = ps->hdr;
-  const uint32_t px_bytes = uint32_t(h.npx) * 4u;
-  const float* irow = ws.imgT + int64_t(h.img) * kImgT;
+  const int phase = ps->phase;
+  ps->slot = (s + 1 == NST) ? 0 : s + 1;
   if (phase == 0) {                                  // L: header | image row | log-depth slice
+    const d3r_align_item* gh = reinterpret_cast<const d3r_align_item*>(D.items) + item;
+    const d3r_align_item h = *gh;
+    const uint32_t px_bytes = uint32_t(h.npx) * 4u;
+    const float* irow = ws.imgT + int64_t(h.img) * kImgT;
     sb_expect_tx(bar, 64u + 64u + px_bytes);
     sb_bulk(dst, gh, 64u, bar);
     sb_bulk(dst + 64u, irow, 64u, bar);
     sb_bulk(dst + kHdrBytes, D.logd + h.pix0, px_bytes, bar);
-  } else if (phase <= h.deg) {                       // E_k: entry row | observations
-    const int k = phase - 1;
-    const uint32_t pay = uint32_t(h.nslots) * kSlotBytes;
+    ps->deg = h.deg; ps->px_bytes = px_bytes; ps->pay_bytes = uint32_t(h.nslots) * kSlotBytes; ps->slab_units = h.slab_units;
+    ps->row = ws.entT + int64_t(h.e0) * kEdgeT;
+    ps->obs = reinterpret_cast<const uint4*>(D.obs) + h.obs0;
+    ps->irow = irow; ps->pix0 = h.pix0;
+    ps->phase = 1;
+  } else if (phase <= ps->deg) {                     // E_k: entry row | observations
+    const float* row = ps->row;
+    const uint4* obs = ps->obs;
+    const uint32_t pay = ps->pay_bytes;
     sb_expect_tx(bar, 48u + pay);
-    sb_bulk(dst, ws.entT + int64_t(h.e0 + k) * kEdgeT, 48u, bar);
-    sb_bulk(dst + kHdrBytes, reinterpret_cast<const uint4*>(D.obs) + (h.obs0 + int64_t(k) * h.slab_units), pay, bar);
+    sb_bulk(dst, row, 48u, bar);
+    sb_bulk(dst + kHdrBytes, obs, pay, bar);
+    ps->row = row + kEdgeT;
+    ps->obs = obs + ps->slab_units;
+    ps->phase = phase + 1;
   } else {                                           // MV: image row | log-depth | exp_avg | exp_avg_sq
+    const uint32_t px_bytes = ps->px_bytes;
+    const int64_t pix0 = ps->pix0;
     sb_expect_tx(bar, 64u + 3u * px_bytes);
-    sb_bulk(dst, irow, 64u, bar);
-    sb_bulk(dst + kHdrBytes, D.logd + h.pix0, px_bytes, bar);
-    sb_bulk(dst + kHdrBytes + PPT * 256, D.logd_m + h.pix0, px_bytes, bar);
-    sb_bulk(dst + kHdrBytes + 2 * PPT * 256, D.logd_v + h.pix0, px_bytes, bar);
+    sb_bulk(dst, ps->irow, 64u, bar);
+    sb_bulk(dst + kHdrBytes, D.logd + pix0, px_bytes, bar);
+    sb_bulk(dst + kHdrBytes + PPT * 256, D.logd_m + pix0, px_bytes, bar);
+    sb_bulk(dst + kHdrBytes + 2 * PPT * 256, D.logd_v + pix0, px_bytes, bar);
+    ps->item = item + 1;
+    ps->phase = 0;
   }
-  if (phase == h.deg + 1) { ps->item = item + 1; phase = 0; } else { ++phase; }
-  ps->phase = phase;
-  ps->slot = (s + 1 == NST) ? 0 : s + 1;
+}
+
+// ---- per-stage math, specialised on the number of slots of the item so that the slots' instruction streams are
+// ---- straight-line code the scheduler can interleave (no per-slot branches)
+template <int NS, int PPT>
+__device__ __forceinline__ void unproject_slots(const uint8_t* slot, int lane, int npx, f2 (&X)[PPT][3], f2 (&G)[PPT][3]) {
+  const d3r_align_item* h = reinterpret_cast<const d3r_align_item*>(slot);
+  const int W = h->W, u0 = h->u0, v0 = h->v0;
+  const float invW = h->inv_w;
+  const float4* ir = reinterpret_cast<const float4*>(slot + 64);
+  const float4 i0 = ir[0], i1 = ir[1], i2 = ir[2], i3 = ir[3];   // R0..R3 | R4..R7 | R8 T0 T1 T2 | ifx ify cx cy
+  const float2* ldp = reinterpret_cast<const float2*>(slot + kHdrBytes);
+#pragma unroll
+  for (int kk = 0; kk < PPT; ++kk) {
+    if (kk < NS) {
+      const int j = kk * 32 + lane;
+      float2 ld = make_float2(0.f, 0.f);
+      if (2 * j < npx) ld = ldp[j];
+      const f2 d = pack2(__expf(ld.x), __expf(ld.y));
+      const int a = u0 + 2 * j;
+      const int dv = __float2int_rz((float(a) + 0.5f) * invW);
+      const int uA = a - dv * W, vA = v0 + dv;
+      int uB = uA + 1, vB = vA;
+      if (uB == W) { uB = 0; vB = vA + 1; }
+      // c0 = d * (u - cx) / fx, c1 = d * (v - cy) / fy   (optimizer.py:203-211)
+      const f2 c0 = mul2(mul2(d, add2(pack2(float(uA), float(uB)), bc2(-i3.z))), bc2(i3.x));
+      const f2 c1 = mul2(mul2(d, add2(pack2(float(vA), float(vB)), bc2(-i3.w))), bc2(i3.y));
+      X[kk][0] = fma2(bc2(i0.x), c0, fma2(bc2(i0.y), c1, fma2(bc2(i0.z), d, bc2(i2.y))));
+      X[kk][1] = fma2(bc2(i0.w), c0, fma2(bc2(i1.x), c1, fma2(bc2(i1.y), d, bc2(i2.z))));
+      X[kk][2] = fma2(bc2(i1.z), c0, fma2(bc2(i1.w), c1, fma2(bc2(i2.x), d, bc2(i2.w))));
+    } else {
+      X[kk][0] = X[kk][1] = X[kk][2] = 0ull;
+    }
+    G[kk][0] = G[kk][1] = G[kk][2] = 0ull;
+  }
+}
+
+template <bool kL2, int NS, int PPT>
+__device__ __forceinline__ void entry_slots(const uint8_t* slot, int lane, const f2 (&X)[PPT][3], f2 (&G)[PPT][3],
+                                            float (&a13)[kEntVals]) {
+  const float4* er = reinterpret_cast<const float4*>(slot);
+  const float4 m0 = er[0], m1 = er[1], m2 = er[2];    // -M0..-M3 | -M4..-M7 | -M8 -t0 -t1 -t2
+  const uint8_t* pay = slot + kHdrBytes + lane * 16;
+  f2 acc[kEntVals];
+#pragma unroll
+  for (int v = 0; v < kEntVals; ++v) acc[v] = 0ull;
+#pragma unroll
+  for (int kk = 0; kk < NS; ++kk) {
+    const ulonglong2 p0 = *reinterpret_cast<const ulonglong2*>(pay + kk * kSlotBytes);
+    const ulonglong2 p1 = *reinterpret_cast<const ulonglong2*>(pay + kk * kSlotBytes + 512);
+    const f2 qx = p0.x, qy = p0.y, qz = p1.x, w = p1.y;
+    // r = X - (M q + t)
+    const f2 r0 = fma2(bc2(m0.x), qx, fma2(bc2(m0.y), qy, fma2(bc2(m0.z), qz, add2(X[kk][0], bc2(m2.y)))));
+    const f2 r1 = fma2(bc2(m0.w), qx, fma2(bc2(m1.x), qy, fma2(bc2(m1.y), qz, add2(X[kk][1], bc2(m2.z)))));
+    const f2 r2 = fma2(bc2(m1.z), qx, fma2(bc2(m1.w), qy, fma2(bc2(m2.x), qz, add2(X[kk][2], bc2(m2.w)))));
+    const f2 rho2 = fma2(r0, r0, fma2(r1, r1, mul2(r2, r2)));
+    f2 gs;
+    if (kL2) {
+      acc[12] = fma2(w, rho2, acc[12]);
+      gs = add2(w, w);
+    } else {
+      // torch's norm backward yields 0 at ||r|| == 0: r == 0 there, so a finite 1/||r|| stand-in gives g = 0
+      float ra, rb;
+      unpack2(rho2, ra, rb);
+      const f2 inv = pack2(rsqrt_approx(fmaxf(ra, 1e-36f)), rsqrt_approx(fmaxf(rb, 1e-36f)));
+      acc[12] = fma2(w, mul2(rho2, inv), acc[12]);
+      gs = mul2(w, inv);
+    }
+    const f2 g0 = mul2(gs, r0), g1 = mul2(gs, r1), g2 = mul2(gs, r2);
+    G[kk][0] = add2(G[kk][0], g0); G[kk][1] = add2(G[kk][1], g1); G[kk][2] = add2(G[kk][2], g2);
+    acc[0] = fma2(g0, qx, acc[0]); acc[1] = fma2(g0, qy, acc[1]); acc[2] = fma2(g0, qz, acc[2]);
+    acc[3] = fma2(g1, qx, acc[3]); acc[4] = fma2(g1, qy, acc[4]); acc[5] = fma2(g1, qz, acc[5]);
+    acc[6] = fma2(g2, qx, acc[6]); acc[7] = fma2(g2, qy, acc[7]); acc[8] = fma2(g2, qz, acc[8]);
+    acc[9] = add2(acc[9], g0); acc[10] = add2(acc[10], g1); acc[11] = add2(acc[11], g2);
+  }
+#pragma unroll
+  for (int v = 0; v < kEntVals; ++v) { float lo, hi; unpack2(acc[v], lo, hi); a13[v] = lo + hi; }
+}
+
+template <int NS, int PPT>
+__device__ __forceinline__ void adam_slots(const d3r_align_desc& D, const uint8_t* slot, int lane, int npx, int64_t pix0,
+                                           float step_size, float inv_bc2s, const f2 (&X)[PPT][3], const f2 (&G)[PPT][3],
+                                           float (&s12)[kImgVals]) {
+  const float4 i2 = reinterpret_cast<const float4*>(slot)[2];   // R8 T0 T1 T2
+  const float2* ldp = reinterpret_cast<const float2*>(slot + kHdrBytes);
+  const float2* mp = reinterpret_cast<const float2*>(slot + kHdrBytes + PPT * 256);
+  const float2* vp = reinterpret_cast<const float2*>(slot + kHdrBytes + 2 * PPT * 256);
+  f2 S[kImgVals];
+#pragma unroll
+  for (int v = 0; v < kImgVals; ++v) S[v] = 0ull;
+#pragma unroll
+  for (int kk = 0; kk < NS; ++kk) {
+    const int j = kk * 32 + lane;
+    if (2 * j < npx) {
+      // Y = X - T = R c ; dX/dlogd = Y (c is linear in the depth)
+      const f2 y0 = add2(X[kk][0], bc2(-i2.y)), y1 = add2(X[kk][1], bc2(-i2.z)), y2 = add2(X[kk][2], bc2(-i2.w));
+      const f2 gd = fma2(G[kk][0], y0, fma2(G[kk][1], y1, mul2(G[kk][2], y2)));
+      S[0] = fma2(G[kk][0], y0, S[0]); S[1] = fma2(G[kk][0], y1, S[1]); S[2] = fma2(G[kk][0], y2, S[2]);
+      S[3] = fma2(G[kk][1], y0, S[3]); S[4] = fma2(G[kk][1], y1, S[4]); S[5] = fma2(G[kk][1], y2, S[5]);
+      S[6] = fma2(G[kk][2], y0, S[6]); S[7] = fma2(G[kk][2], y1, S[7]); S[8] = fma2(G[kk][2], y2, S[8]);
+      S[9] = add2(S[9], G[kk][0]); S[10] = add2(S[10], G[kk][1]); S[11] = add2(S[11], G[kk][2]);
+      const float2 ld = ldp[j], mm = mp[j], vv = vp[j];
+      // torch.optim.Adam: m += (1-b1)(g-m); v = v*b2 + (1-b2) g g; p -= step * m / (sqrt(v)/sqrt(bc2) + eps)
+      const f2 m_old = pack2(mm.x, mm.y);
+      const f2 m_new = fma2(bc2(1.f - D.beta1), fma2(bc2(-1.f), m_old, gd), m_old);
+      const f2 v_new = fma2(mul2(bc2(1.f - D.beta2), gd), gd, mul2(pack2(vv.x, vv.y), bc2(D.beta2)));
+      float va, vb;
+      unpack2(v_new, va, vb);
+      const f2 denom = fma2(pack2(sqrt_approx(va), sqrt_approx(vb)), bc2(inv_bc2s), bc2(D.adam_eps));
+      float da, db;
+      unpack2(denom, da, db);
+      const f2 upd = mul2(m_new, pack2(rcp_approx(da), rcp_approx(db)));
+      const f2 ld_new = fma2(bc2(-step_size), upd, pack2(ld.x, ld.y));
+      reinterpret_cast<f2*>(D.logd + pix0)[j] = ld_new;
+      reinterpret_cast<f2*>(D.logd_m + pix0)[j] = m_new;
+      reinterpret_cast<f2*>(D.logd_v + pix0)[j] = v_new;
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < kImgVals; ++v) { float lo, hi; unpack2(S[v], lo, hi); s12[v] = lo + hi; }
 }
 
 template <bool kL2, int PPT, int NST>
 __global__ void __launch_bounds__(kSThreads, 2)
 align_stream_kernel(const __grid_constant__ d3r_align_desc D, int it) {
+  static_assert(PPT == 3, "the per-slot specialisations below are written for 3 slots per item");
   constexpr int kStage = kHdrBytes + PPT * kSlotBytes;
   extern __shared__ __align__(128) uint8_t s_dyn[];
   __shared__ __align__(8) uint64_t s_full[kSWarps][NST];
@@ -177,7 +314,7 @@ align_stream_kernel(const __grid_constant__ d3r_align_desc D, int it) {
   int si = 0;                           // ring slot of the next stage to consume
   uint32_t par = 0;                     // its mbarrier phase parity
   auto advance = [&]() { if (++si == NST) { si = 0; par ^= 1u; } };
-  int acc_e0 = 0, acc_w0 = 0, acc_cnt = 0, acc_img = -1;   // open entry window of s_acc
+  int acc_e0 = 0, acc_cnt = 0, acc_img = -1;               // open entry window of s_acc: entries [acc_e0, acc_e0 + acc_cnt)
   int simg = -1;                                           // image of s_img
 
   auto flush_entries = [&]() {
@@ -185,7 +322,7 @@ align_stream_kernel(const __grid_constant__ d3r_align_desc D, int it) {
       for (int idx = lane; idx < acc_cnt * kEntVals; idx += 32) {
         const float v = s_acc[idx];
         s_acc[idx] = 0.f;
-        fix_add(ws.ent_acc + int64_t(acc_e0 + acc_w0) * kEntVals + idx, v, ws.flags);
+        fix_add(ws.ent_acc + int64_t(acc_e0) * kEntVals + idx, v, ws.flags);
       }
       __syncwarp();
     }
@@ -208,92 +345,33 @@ align_stream_kernel(const __grid_constant__ d3r_align_desc D, int it) {
     const int img = h->img, nslots = h->nslots, npx = h->npx, e0 = h->e0, deg = h->deg;
     const int64_t pix0 = h->pix0;
     f2 X[PPT][3], G[PPT][3];
-    {
-      const int W = h->W, u0 = h->u0, v0 = h->v0;
-      const float invW = h->inv_w;
-      const float4* ir = reinterpret_cast<const float4*>(slot + 64);
-      const float4 i0 = ir[0], i1 = ir[1], i2 = ir[2], i3 = ir[3];   // R0..R3 | R4..R7 | R8 T0 T1 T2 | ifx ify cx cy
-      const float2* ldp = reinterpret_cast<const float2*>(slot + kHdrBytes);
-#pragma unroll
-      for (int kk = 0; kk < PPT; ++kk) {
-        if (kk < nslots) {
-          const int j = kk * 32 + lane;
-          float2 ld = make_float2(0.f, 0.f);
-          if (2 * j < npx) ld = ldp[j];
-          const f2 d = pack2(__expf(ld.x), __expf(ld.y));
-          const int a = u0 + 2 * j;
-          const int dv = __float2int_rz((float(a) + 0.5f) * invW);
-          const int uA = a - dv * W, vA = v0 + dv;
-          int uB = uA + 1, vB = vA;
-          if (uB == W) { uB = 0; vB = vA + 1; }
-          // c0 = d * (u - cx) / fx, c1 = d * (v - cy) / fy   (optimizer.py:203-211)
-          const f2 c0 = mul2(mul2(d, add2(pack2(float(uA), float(uB)), bc2(-i3.z))), bc2(i3.x));
-          const f2 c1 = mul2(mul2(d, add2(pack2(float(vA), float(vB)), bc2(-i3.w))), bc2(i3.y));
-          X[kk][0] = fma2(bc2(i0.x), c0, fma2(bc2(i0.y), c1, fma2(bc2(i0.z), d, bc2(i2.y))));
-          X[kk][1] = fma2(bc2(i0.w), c0, fma2(bc2(i1.x), c1, fma2(bc2(i1.y), d, bc2(i2.z))));
-          X[kk][2] = fma2(bc2(i1.z), c0, fma2(bc2(i1.w), c1, fma2(bc2(i2.x), d, bc2(i2.w))));
-        } else {
-          X[kk][0] = X[kk][1] = X[kk][2] = 0ull;
-        }
-        G[kk][0] = G[kk][1] = G[kk][2] = 0ull;
-      }
-    }
+    if (nslots == 3) unproject_slots<3, PPT>(slot, lane, npx, X, G);
+    else if (nslots == 2) unproject_slots<2, PPT>(slot, lane, npx, X, G);
+    else unproject_slots<1, PPT>(slot, lane, npx, X, G);
     __syncwarp();
     if (lane == 0) produce_next<PPT, NST>(D, ws, ps, ring, full);
     advance();
 
     if (simg != img) { flush_image(); simg = img; }
+    // a window that holds ALL entries of the image stays open across the warp's items of that image
+    if (acc_img != img || acc_e0 != e0 || acc_cnt == 0) {
+      flush_entries();
+      acc_img = img; acc_e0 = e0; acc_cnt = min(Wn, deg);
+    }
 
     // ------------------------------------------------------------------ E stages: residuals against every entry
-    int w0 = 0, kin = 0;                 // window start / index inside the window of entry k
+    int kin = 0;                          // index of entry k inside the open window
     for (int k = 0; k < deg; ++k, ++kin) {
-      if (kin == Wn) { w0 += Wn; kin = 0; }
-      if (acc_img != img || acc_w0 != w0 || acc_cnt == 0) {
+      if (kin == Wn) {                    // more entries than the window holds: spill and open the next window
         flush_entries();
-        acc_img = img; acc_e0 = e0; acc_w0 = w0; acc_cnt = min(Wn, deg - w0);
+        acc_e0 = e0 + k; acc_cnt = min(Wn, deg - k); kin = 0;
       }
       slot = ring + si * kStage;
       sb_wait(s_u32(&full[si]), par);
-      const float4* er = reinterpret_cast<const float4*>(slot);
-      const float4 m0 = er[0], m1 = er[1], m2 = er[2];    // -M0..-M3 | -M4..-M7 | -M8 -t0 -t1 -t2
-      const uint8_t* pay = slot + kHdrBytes + lane * 16;
-      f2 acc[kEntVals];
-#pragma unroll
-      for (int v = 0; v < kEntVals; ++v) acc[v] = 0ull;
-#pragma unroll
-      for (int kk = 0; kk < PPT; ++kk) {
-        if (kk < nslots) {
-          const ulonglong2 p0 = *reinterpret_cast<const ulonglong2*>(pay + kk * kSlotBytes);
-          const ulonglong2 p1 = *reinterpret_cast<const ulonglong2*>(pay + kk * kSlotBytes + 512);
-          const f2 qx = p0.x, qy = p0.y, qz = p1.x, w = p1.y;
-          // r = X - (M q + t)
-          const f2 r0 = fma2(bc2(m0.x), qx, fma2(bc2(m0.y), qy, fma2(bc2(m0.z), qz, add2(X[kk][0], bc2(m2.y)))));
-          const f2 r1 = fma2(bc2(m0.w), qx, fma2(bc2(m1.x), qy, fma2(bc2(m1.y), qz, add2(X[kk][1], bc2(m2.z)))));
-          const f2 r2 = fma2(bc2(m1.z), qx, fma2(bc2(m1.w), qy, fma2(bc2(m2.x), qz, add2(X[kk][2], bc2(m2.w)))));
-          const f2 rho2 = fma2(r0, r0, fma2(r1, r1, mul2(r2, r2)));
-          f2 gs;
-          if (kL2) {
-            acc[12] = fma2(w, rho2, acc[12]);
-            gs = add2(w, w);
-          } else {
-            // torch's norm backward yields 0 at ||r|| == 0: r == 0 there, so a finite 1/||r|| stand-in gives g = 0
-            float ra, rb;
-            unpack2(rho2, ra, rb);
-            const f2 inv = pack2(rsqrt_approx(fmaxf(ra, 1e-36f)), rsqrt_approx(fmaxf(rb, 1e-36f)));
-            acc[12] = fma2(w, mul2(rho2, inv), acc[12]);
-            gs = mul2(w, inv);
-          }
-          const f2 g0 = mul2(gs, r0), g1 = mul2(gs, r1), g2 = mul2(gs, r2);
-          G[kk][0] = add2(G[kk][0], g0); G[kk][1] = add2(G[kk][1], g1); G[kk][2] = add2(G[kk][2], g2);
-          acc[0] = fma2(g0, qx, acc[0]); acc[1] = fma2(g0, qy, acc[1]); acc[2] = fma2(g0, qz, acc[2]);
-          acc[3] = fma2(g1, qx, acc[3]); acc[4] = fma2(g1, qy, acc[4]); acc[5] = fma2(g1, qz, acc[5]);
-          acc[6] = fma2(g2, qx, acc[6]); acc[7] = fma2(g2, qy, acc[7]); acc[8] = fma2(g2, qz, acc[8]);
-          acc[9] = add2(acc[9], g0); acc[10] = add2(acc[10], g1); acc[11] = add2(acc[11], g2);
-        }
-      }
       float a13[kEntVals];
-#pragma unroll
-      for (int v = 0; v < kEntVals; ++v) { float lo, hi; unpack2(acc[v], lo, hi); a13[v] = lo + hi; }
+      if (nslots == 3) entry_slots<kL2, 3, PPT>(slot, lane, X, G, a13);
+      else if (nslots == 2) entry_slots<kL2, 2, PPT>(slot, lane, X, G, a13);
+      else entry_slots<kL2, 1, PPT>(slot, lane, X, G, a13);
       __syncwarp();                               // every lane is done reading the observations of this stage
       const float tot = warp_transpose_sum<kEntVals>(a13, reinterpret_cast<float*>(slot + kHdrBytes), lane);
       if (!(lane & 1) && lane < 2 * kEntVals) s_acc[kin * kEntVals + (lane >> 1)] += tot;
@@ -307,44 +385,10 @@ align_stream_kernel(const __grid_constant__ d3r_align_desc D, int it) {
     slot = ring + si * kStage;
     sb_wait(s_u32(&full[si]), par);
     if (train) {
-      const float4 i2 = reinterpret_cast<const float4*>(slot + 64 - 64)[2];   // R8 T0 T1 T2
-      const float2* ldp = reinterpret_cast<const float2*>(slot + kHdrBytes);
-      const float2* mp = reinterpret_cast<const float2*>(slot + kHdrBytes + PPT * 256);
-      const float2* vp = reinterpret_cast<const float2*>(slot + kHdrBytes + 2 * PPT * 256);
-      f2 S[kImgVals];
-#pragma unroll
-      for (int v = 0; v < kImgVals; ++v) S[v] = 0ull;
-#pragma unroll
-      for (int kk = 0; kk < PPT; ++kk) {
-        const int j = kk * 32 + lane;
-        if (kk < nslots && 2 * j < npx) {
-          // Y = X - T = R c ; dX/dlogd = Y (c is linear in the depth)
-          const f2 y0 = add2(X[kk][0], bc2(-i2.y)), y1 = add2(X[kk][1], bc2(-i2.z)), y2 = add2(X[kk][2], bc2(-i2.w));
-          const f2 gd = fma2(G[kk][0], y0, fma2(G[kk][1], y1, mul2(G[kk][2], y2)));
-          S[0] = fma2(G[kk][0], y0, S[0]); S[1] = fma2(G[kk][0], y1, S[1]); S[2] = fma2(G[kk][0], y2, S[2]);
-          S[3] = fma2(G[kk][1], y0, S[3]); S[4] = fma2(G[kk][1], y1, S[4]); S[5] = fma2(G[kk][1], y2, S[5]);
-          S[6] = fma2(G[kk][2], y0, S[6]); S[7] = fma2(G[kk][2], y1, S[7]); S[8] = fma2(G[kk][2], y2, S[8]);
-          S[9] = add2(S[9], G[kk][0]); S[10] = add2(S[10], G[kk][1]); S[11] = add2(S[11], G[kk][2]);
-          const float2 ld = ldp[j], mm = mp[j], vv = vp[j];
-          // torch.optim.Adam: m += (1-b1)(g-m); v = v*b2 + (1-b2) g g; p -= step * m / (sqrt(v)/sqrt(bc2) + eps)
-          const f2 m_old = pack2(mm.x, mm.y);
-          const f2 m_new = fma2(bc2(1.f - D.beta1), fma2(bc2(-1.f), m_old, gd), m_old);
-          const f2 v_new = fma2(mul2(bc2(1.f - D.beta2), gd), gd, mul2(pack2(vv.x, vv.y), bc2(D.beta2)));
-          float va, vb;
-          unpack2(v_new, va, vb);
-          const f2 denom = fma2(pack2(sqrt_approx(va), sqrt_approx(vb)), bc2(inv_bc2s), bc2(D.adam_eps));
-          float da, db;
-          unpack2(denom, da, db);
-          const f2 upd = mul2(m_new, pack2(rcp_approx(da), rcp_approx(db)));
-          const f2 ld_new = fma2(bc2(-step_size), upd, pack2(ld.x, ld.y));
-          reinterpret_cast<f2*>(D.logd + pix0)[j] = ld_new;
-          reinterpret_cast<f2*>(D.logd_m + pix0)[j] = m_new;
-          reinterpret_cast<f2*>(D.logd_v + pix0)[j] = v_new;
-        }
-      }
       float s12[kImgVals];
-#pragma unroll
-      for (int v = 0; v < kImgVals; ++v) { float lo, hi; unpack2(S[v], lo, hi); s12[v] = lo + hi; }
+      if (nslots == 3) adam_slots<3, PPT>(D, slot, lane, npx, pix0, step_size, inv_bc2s, X, G, s12);
+      else if (nslots == 2) adam_slots<2, PPT>(D, slot, lane, npx, pix0, step_size, inv_bc2s, X, G, s12);
+      else adam_slots<1, PPT>(D, slot, lane, npx, pix0, step_size, inv_bc2s, X, G, s12);
       __syncwarp();
       const float tot = warp_transpose_sum<kImgVals>(s12, reinterpret_cast<float*>(slot + kHdrBytes), lane);
       if (!(lane & 1) && lane < 2 * kImgVals) s_img[lane >> 1] += tot;
@@ -353,14 +397,19 @@ align_stream_kernel(const __grid_constant__ d3r_align_desc D, int it) {
     __syncwarp();
     if (lane == 0) produce_next<PPT, NST>(D, ws, ps, ring, full);
     advance();
+    if (deg > Wn) flush_entries();        // a spilled image starts its next item from window 0 again
   }
   flush_entries();
   flush_image();
 
   // ---- grid ticket: the last CTA to finish runs the small-parameter step ----
-  __threadfence();
+  // every warp's atomics are ordered before the barrier at CTA scope; thread 0's fence then makes them visible at GPU
+  // scope before the ticket (fence cumulativity), so one fence per CTA suffices
   __syncthreads();
-  if (tid == 0) s_flag = (atomicAdd(D.counters, 1) == int(gridDim.x) - 1);
+  if (tid == 0) {
+    __threadfence();
+    s_flag = (atomicAdd(D.counters, 1) == int(gridDim.x) - 1);
+  }
   __syncthreads();
   if (!s_flag) return;
   __threadfence();
