@@ -355,30 +355,24 @@ def main():
     g = torch.Generator(device='cpu').manual_seed(1234 + rank)
     imgs = (torch.rand((2 * B, 3, H, W), generator=g) * 2 - 1).to(device)
     idx1, idx2 = np.arange(B, dtype=np.int32), B + np.arange(B, dtype=np.int32)
-    gather = dict(bufs=None, work=[None, None], flat=[None, None], i=0)
+    # the one collective of the path (N > 1): dust3r_b200.distributed.PairOutputGather -- the same object inference_sharded()
+    # uses: this rank's {pts3d, conf} x 2 rows (6.29 MB / pair) are packed into one send buffer and ONE all_gather_into_tensor
+    # rebuilds the full result on every rank.  depth=2 + async_op: the gather of step k overlaps the forward of step k+1 on
+    # NVLink/NVSwitch; a slot is waited for right before it is reused and all of them at the end of the timed region.
+    gather = None
+    if world > 1:
+        from dust3r_b200.distributed import PairOutputGather
+        gather = PairOutputGather(world * B, (H, W), (H, W), True, device, depth=2)
 
     def step():
         r1, r2 = packed.forward(imgs, idx1, idx2, B, H, W)
-        if world > 1:
-            # the one collective of the path: all-gather of {pts3d, conf} x 2 (6.29 MB / pair).  It is issued
-            # asynchronously into one of two buffers, so it overlaps the next step's compute on NVLink/NVSwitch;
-            # a buffer is waited for right before it is reused (and all of them at the end of the timed region).
-            k = gather['i'] & 1
-            if gather['work'][k] is not None:
-                gather['work'][k].wait()
-            flat = torch.cat((r1['pts3d'].reshape(B, -1), r1['conf'].reshape(B, -1), r2['pts3d'].reshape(B, -1), r2['conf'].reshape(B, -1)), dim=1)
-            if gather['bufs'] is None:
-                gather['bufs'] = [torch.empty((world,) + tuple(flat.shape), dtype=flat.dtype, device=device) for _ in range(2)]
-            gather['flat'][k] = flat
-            gather['work'][k] = dist.all_gather_into_tensor(gather['bufs'][k], flat, async_op=True)
-            gather['i'] += 1
+        if gather is not None:
+            gather.gather(r1, r2, async_op=True)
         return r1, r2
 
     def drain():
-        for k in range(2):
-            if gather['work'][k] is not None:
-                gather['work'][k].wait()
-                gather['work'][k] = None
+        if gather is not None:
+            gather.wait()
 
     W_ = max(args.warmup, 3)
     for _ in range(W_):
@@ -450,7 +444,7 @@ def main():
                 data='synthetic',
                 config=dict(workload=f'{B} synthetic 512x384 pairs per GPU per step ({world * B} total), '
                                      'ViTLarge_BaseDecoder_512_dpt forward only, not symmetrised (encoder sees 2 images/pair)'
-                                     + (', + NCCL all-gather of pointmaps (async, overlapped with the next step)' if world > 1 else ''),
+                                     + (', + the single NCCL all-gather of pointmaps of inference_sharded (PairOutputGather, async, overlapped with the next step)' if world > 1 else ''),
                             weights='random init (synthetic, seed 0)', compute='bf16 operands / fp32 accumulate / fp32 residual stream',
                             l2='activations per step (>5 GB) exceed the 126 MB L2; no explicit flush needed',
                             parallelism=f'dp{world}'),

@@ -116,7 +116,8 @@ __device__ __forceinline__ unsigned long long gtime() {
   return t;
 }
 
-#define D3R_TSTAMP(i) do { if (g_align_dbg && threadIdx.x == 0) g_align_dbg[4 * size_t(D.n_chunks) + (i)] = gtime(); } while (0)
+// small-step stamps follow the per-CTA (general kernel) / per-warp (streaming kernel) rows
+#define D3R_TSTAMP(i) do { if (g_align_dbg && threadIdx.x == 0) g_align_dbg[4 * size_t(D.stream_kernel ? D.stream_grid * 8 : D.n_chunks) + (i)] = gtime(); } while (0)
 
 // ---- derived transforms / small-parameter step (run by ONE CTA while the rest of the chip idles) ----------
 // Written for latency: independent global loads are issued together, block reductions cost one barrier (every

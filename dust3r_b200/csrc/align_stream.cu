@@ -292,6 +292,8 @@ align_stream_kernel(const __grid_constant__ d3r_align_desc D, int it) {
   ProdState* ps = &s_prod[warp];
 
   const int ib = D.warp_item_ptr[gw], ie = D.warp_item_ptr[gw + 1];
+  unsigned long long* dbg = g_align_dbg ? g_align_dbg + 4 * size_t(gw) : nullptr;   // per-warp timeline (debug aid)
+  if (dbg && lane == 0) dbg[0] = gtime();
   if (lane == 0) {
     for (int s = 0; s < NST; ++s) sb_init(s_u32(&full[s]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -303,6 +305,7 @@ align_stream_kernel(const __grid_constant__ d3r_align_desc D, int it) {
   // everything below reads what the previous iteration wrote (transforms, log-depths, Adam moments)
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (dbg && lane == 0) dbg[1] = gtime();
   if (lane == 0)
     for (int s = 0; s < NST; ++s) produce_next<PPT, NST>(D, ws, ps, ring, full);
   __syncwarp();
@@ -401,6 +404,7 @@ align_stream_kernel(const __grid_constant__ d3r_align_desc D, int it) {
   }
   flush_entries();
   flush_image();
+  if (dbg && lane == 0) dbg[2] = gtime();
 
   // ---- grid ticket: the last CTA to finish runs the small-parameter step ----
   // every warp's atomics are ordered before the barrier at CTA scope; thread 0's fence then makes them visible at GPU
@@ -411,10 +415,12 @@ align_stream_kernel(const __grid_constant__ d3r_align_desc D, int it) {
     s_flag = (atomicAdd(D.counters, 1) == int(gridDim.x) - 1);
   }
   __syncthreads();
+  if (dbg && lane == 0) dbg[3] = gtime();
   if (!s_flag) return;
   __threadfence();
   if (tid == 0) D.counters[0] = 0;   // re-arm for the next launch
   small_param_step(D, ws, it, s_red);
+  D3R_TSTAMP(5);
 }
 
 // ---- one launch packs every entry (device-resident forward output -> observation layout) ----------------------
