@@ -35,6 +35,7 @@ class AlignDesc(C.Structure):
         ('workspace', C.c_void_p), ('sched', C.c_void_p), ('loss_out', C.c_void_p), ('counters', C.c_void_p),
         ('stream_kernel', C.c_int32), ('stream_grid', C.c_int32), ('stream_ppt', C.c_int32), ('stream_window', C.c_int32),
         ('n_items', C.c_int32), ('reserved0', C.c_int32), ('items', C.c_void_p), ('warp_item_ptr', C.c_void_p),
+        ('items_rev', C.c_void_p), ('warp_item_ptr_rev', C.c_void_p),
     ]
 
 

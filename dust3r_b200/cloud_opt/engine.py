@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import List, Sequence, Tuple
 
 import numpy as np
@@ -77,7 +78,7 @@ class AlignEngine:
                  pred_i: Sequence[torch.Tensor], pred_j: Sequence[torch.Tensor],
                  conf_i: Sequence[torch.Tensor], conf_j: Sequence[torch.Tensor],
                  device, conf_mode='log', dist='l1', variant='stacked', pix_stride=None,
-                 base_scale=0.5, pw_break=20.0, focal_break=20.0, kernel='auto'):
+                 base_scale=0.5, pw_break=20.0, focal_break=20.0, kernel='auto', reverse_odd='auto'):
         self.device = _lib.require_cuda_device(device)
         self.lib = _lib.get_lib()
         self.edges = [(int(i), int(j)) for i, j in edges]
@@ -107,6 +108,9 @@ class AlignEngine:
         assert kernel in ('stream', 'general')
         self.kernel = kernel
         stream = kernel == 'stream'
+        if reverse_odd == 'auto':     # D3R_ALIGN_REVERSE=0: every iteration walks the items in the same order (A/B switch)
+            reverse_odd = os.environ.get('D3R_ALIGN_REVERSE', '1') != '0'
+        self.reverse_odd = bool(reverse_odd)
         chunk = self._pick_chunk_px(areas)
         self.chunk_px = chunk
         nchunks = [(a + chunk - 1) // chunk for a in areas]
@@ -205,7 +209,7 @@ class AlignEngine:
 
     def _no_items(self):
         self.stream_grid = self.stream_ppt = self.stream_window = self.n_items = 0
-        self._items = self._warp_item_ptr = None
+        self._items = self._warp_item_ptr = self._items_rev = self._warp_item_ptr_rev = None
 
     def _build_items(self, ent_ptr, ent_obs_off, slots):
         lib = self.lib
@@ -218,6 +222,14 @@ class AlignEngine:
         self._items = torch.from_numpy(arr.view(np.uint8)).to(dev)
         self._warp_item_ptr = torch.from_numpy(warp_ptr).to(dev)
         self.n_items = len(arr)
+        # reversed traversal for odd iterations: warp w walks the reverse of warp (nw-1-w)'s run, so the global streaming
+        # order of an odd iteration is the exact reverse of an even one (the L2 still holds the tail of the last pass)
+        self._items_rev = self._warp_item_ptr_rev = None
+        if self.reverse_odd:
+            arr_rev = np.ascontiguousarray(arr[::-1])
+            warp_ptr_rev = (len(arr) - warp_ptr[::-1]).astype(np.int32)
+            self._items_rev = torch.from_numpy(arr_rev.view(np.uint8)).to(dev)
+            self._warp_item_ptr_rev = torch.from_numpy(np.ascontiguousarray(warp_ptr_rev)).to(dev)
         self.stream_grid, self.stream_ppt = grid, ppt
         deg_max = int(np.diff(ent_ptr).max())
         self.stream_window = int(min(max(deg_max, 1), lib.d3r_align_stream_max_window()))
@@ -333,9 +345,12 @@ class AlignEngine:
         d.loss_out = self.loss_out.data_ptr()
         d.counters = self.counters.data_ptr()
         d.stream_kernel = 1 if self.kernel == 'stream' else 0
+        d.reserved0 = int(os.environ.get('D3R_ALIGN_FLAGS', '0'))   # debug A/B switches of the streaming kernel
         d.stream_grid, d.stream_ppt, d.stream_window, d.n_items = self.stream_grid, self.stream_ppt, self.stream_window, self.n_items
         if self.kernel == 'stream':
             d.items, d.warp_item_ptr = self._items.data_ptr(), self._warp_item_ptr.data_ptr()
+            if self._items_rev is not None:
+                d.items_rev, d.warp_item_ptr_rev = self._items_rev.data_ptr(), self._warp_item_ptr_rev.data_ptr()
         return d
 
     def prepare(self):

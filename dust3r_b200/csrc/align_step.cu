@@ -300,19 +300,18 @@ align_iter_kernel(const __grid_constant__ d3r_align_desc D, int it) {
   }
   if (dbg && tid == 0) dbg[1] = gtime();
 
+  prefetch_small_step_inputs(D, ws, it, int((size_t(kStages) * PPT * kThreads * sizeof(float4)) / 4), tid, kThreads);
   // ---- grid ticket: the last CTA to finish runs the small-parameter step ----
-  __threadfence();
   __syncthreads();
-  if (tid == 0) s_flag = (atomicAdd(D.counters, 1) == int(gridDim.x) - 1);
+  if (tid == 0) s_flag = (grid_ticket(D.counters) == int(gridDim.x) - 1);
   __syncthreads();
   if (!s_flag) {
     if (dbg && tid == 0) dbg[2] = gtime();
     return;
   }
-  __threadfence();
   if (tid == 0) D.counters[0] = 0;   // re-arm for the next launch
   if (dbg && tid == 0) dbg[2] = gtime();
-  small_param_step(D, ws, it, s_red);
+  small_step(D, ws, it, s_red, reinterpret_cast<float*>(s_dyn), int((size_t(kStages) * PPT * kThreads * sizeof(float4)) / 4));
   if (dbg && tid == 0) dbg[3] = gtime();
 }
 
@@ -346,7 +345,10 @@ __global__ void pack_obs_kernel(const float* __restrict__ pts, const float* __re
 }  // namespace align
 }  // namespace d3r
 
-namespace d3r { namespace align { int launch_stream(const d3r_align_desc* desc, int it_begin, int it_end, cudaStream_t st); } }
+namespace d3r { namespace align {
+int launch_stream(const d3r_align_desc* desc, int it_begin, int it_end, cudaStream_t st);
+int stream_set_debug(unsigned long long* p);
+} }
 
 using namespace d3r;
 using namespace d3r::align;
@@ -354,7 +356,7 @@ using namespace d3r::align;
 extern "C" int d3r_align_set_debug(void* dev_buf) {
   unsigned long long* p = reinterpret_cast<unsigned long long*>(dev_buf);
   D3R_CUDA(cudaMemcpyToSymbol(g_align_dbg, &p, sizeof(p)));
-  return D3R_OK;
+  return stream_set_debug(p);
 }
 
 extern "C" int d3r_align_chunk_pixels(void) { return kChunk; }

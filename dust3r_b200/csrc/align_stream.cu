@@ -69,6 +69,21 @@ __device__ __forceinline__ void sb_bulk(uint32_t dst, const void* src, uint32_t 
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// Streamed data (observations, log-depths, Adam moments) is loaded with the L2 evict_first policy: it is dead after one use
+// within an iteration, and at default priority 200+ MB of it per iteration push everything else out of the 126 MB L2 --
+// including the instructions and inputs of the small-parameter step, which one CTA then re-fetches from DRAM on the critical
+// path.  Among themselves evict_first lines still age in order, so the reversed traversal of odd iterations keeps finding the
+// tail of the previous pass.
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void sb_bulk_stream(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+
 struct ProdState {          // per warp, touched by lane 0 only
   int item, item_end;
   int phase, deg;           // stage to issue next: 0 = L, 1..deg = E_{phase-1}, deg+1 = MV
@@ -101,8 +116,8 @@ __device__ __forceinline__ float warp_transpose_sum(const float (&a)[NV], float*
 
 // Issues the next stage of this warp's sequence into its ring slot (lane 0 only).
 template <int PPT, int NST>
-__device__ __forceinline__ void produce_next(const d3r_align_desc& D, const Workspace& ws, ProdState* ps, uint8_t* ring,
-                                             uint64_t* full) {
+__device__ __forceinline__ void produce_next(const d3r_align_desc& D, const Workspace& ws, const d3r_align_item* item_tab,
+                                             ProdState* ps, uint8_t* ring, uint64_t* full) {
   constexpr int kStage = kHdrBytes + PPT * kSlotBytes;
   const int item = ps->item;
   if (item >= ps->item_end) return;
@@ -110,16 +125,17 @@ __device__ __forceinline__ void produce_next(const d3r_align_desc& D, const Work
   const uint32_t dst = s_u32(ring + s * kStage);
   const uint32_t bar = s_u32(&full[s]);
   const int phase = ps->phase;
+  const uint64_t pol = policy_evict_first();
   ps->slot = (s + 1 == NST) ? 0 : s + 1;
   if (phase == 0) {                                  // L: header | image row | log-depth slice
-    const d3r_align_item* gh = reinterpret_cast<const d3r_align_item*>(D.items) + item;
+    const d3r_align_item* gh = item_tab + item;
     const d3r_align_item h = *gh;
     const uint32_t px_bytes = uint32_t(h.npx) * 4u;
     const float* irow = ws.imgT + int64_t(h.img) * kImgT;
     sb_expect_tx(bar, 64u + 64u + px_bytes);
     sb_bulk(dst, gh, 64u, bar);
     sb_bulk(dst + 64u, irow, 64u, bar);
-    sb_bulk(dst + kHdrBytes, D.logd + h.pix0, px_bytes, bar);
+    sb_bulk_stream(dst + kHdrBytes, D.logd + h.pix0, px_bytes, bar, pol);
     ps->deg = h.deg; ps->px_bytes = px_bytes; ps->pay_bytes = uint32_t(h.nslots) * kSlotBytes; ps->slab_units = h.slab_units;
     ps->row = ws.entT + int64_t(h.e0) * kEdgeT;
     ps->obs = reinterpret_cast<const uint4*>(D.obs) + h.obs0;
@@ -131,7 +147,7 @@ __device__ __forceinline__ void produce_next(const d3r_align_desc& D, const Work
     const uint32_t pay = ps->pay_bytes;
     sb_expect_tx(bar, 48u + pay);
     sb_bulk(dst, row, 48u, bar);
-    sb_bulk(dst + kHdrBytes, obs, pay, bar);
+    sb_bulk_stream(dst + kHdrBytes, obs, pay, bar, pol);
     ps->row = row + kEdgeT;
     ps->obs = obs + ps->slab_units;
     ps->phase = phase + 1;
@@ -140,9 +156,9 @@ __device__ __forceinline__ void produce_next(const d3r_align_desc& D, const Work
     const int64_t pix0 = ps->pix0;
     sb_expect_tx(bar, 64u + 3u * px_bytes);
     sb_bulk(dst, ps->irow, 64u, bar);
-    sb_bulk(dst + kHdrBytes, D.logd + pix0, px_bytes, bar);
-    sb_bulk(dst + kHdrBytes + PPT * 256, D.logd_m + pix0, px_bytes, bar);
-    sb_bulk(dst + kHdrBytes + 2 * PPT * 256, D.logd_v + pix0, px_bytes, bar);
+    sb_bulk_stream(dst + kHdrBytes, D.logd + pix0, px_bytes, bar, pol);
+    sb_bulk_stream(dst + kHdrBytes + PPT * 256, D.logd_m + pix0, px_bytes, bar, pol);
+    sb_bulk_stream(dst + kHdrBytes + 2 * PPT * 256, D.logd_v + pix0, px_bytes, bar, pol);
     ps->item = item + 1;
     ps->phase = 0;
   }
@@ -291,7 +307,11 @@ align_stream_kernel(const __grid_constant__ d3r_align_desc D, int it) {
   uint64_t* full = s_full[warp];
   ProdState* ps = &s_prod[warp];
 
-  const int ib = D.warp_item_ptr[gw], ie = D.warp_item_ptr[gw + 1];
+  // odd iterations walk the reversed item table when the host provides one (L2 reuse across iterations)
+  const bool rev = (it & 1) && D.items_rev != nullptr;
+  const int32_t* wip = rev ? D.warp_item_ptr_rev : D.warp_item_ptr;
+  const d3r_align_item* item_tab = reinterpret_cast<const d3r_align_item*>(rev ? D.items_rev : D.items);
+  const int ib = wip[gw], ie = wip[gw + 1];
   unsigned long long* dbg = g_align_dbg ? g_align_dbg + 4 * size_t(gw) : nullptr;   // per-warp timeline (debug aid)
   if (dbg && lane == 0) dbg[0] = gtime();
   if (lane == 0) {
@@ -307,7 +327,7 @@ align_stream_kernel(const __grid_constant__ d3r_align_desc D, int it) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (dbg && lane == 0) dbg[1] = gtime();
   if (lane == 0)
-    for (int s = 0; s < NST; ++s) produce_next<PPT, NST>(D, ws, ps, ring, full);
+    for (int s = 0; s < NST; ++s) produce_next<PPT, NST>(D, ws, item_tab, ps, ring, full);
   __syncwarp();
 
   const float step_size = D.sched[it * 4 + 1];
@@ -352,7 +372,7 @@ align_stream_kernel(const __grid_constant__ d3r_align_desc D, int it) {
     else if (nslots == 2) unproject_slots<2, PPT>(slot, lane, npx, X, G);
     else unproject_slots<1, PPT>(slot, lane, npx, X, G);
     __syncwarp();
-    if (lane == 0) produce_next<PPT, NST>(D, ws, ps, ring, full);
+    if (lane == 0) produce_next<PPT, NST>(D, ws, item_tab, ps, ring, full);
     advance();
 
     if (simg != img) { flush_image(); simg = img; }
@@ -380,7 +400,7 @@ align_stream_kernel(const __grid_constant__ d3r_align_desc D, int it) {
       if (!(lane & 1) && lane < 2 * kEntVals) s_acc[kin * kEntVals + (lane >> 1)] += tot;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) produce_next<PPT, NST>(D, ws, ps, ring, full);
+      if (lane == 0) produce_next<PPT, NST>(D, ws, item_tab, ps, ring, full);
       advance();
     }
 
@@ -398,28 +418,25 @@ align_stream_kernel(const __grid_constant__ d3r_align_desc D, int it) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncwarp();
-    if (lane == 0) produce_next<PPT, NST>(D, ws, ps, ring, full);
+    if (lane == 0) produce_next<PPT, NST>(D, ws, item_tab, ps, ring, full);
     advance();
     if (deg > Wn) flush_entries();        // a spilled image starts its next item from window 0 again
   }
   flush_entries();
   flush_image();
   if (dbg && lane == 0) dbg[2] = gtime();
+  const int scr_floats = int(size_t(kSWarps) * per_warp / 4);
+  if (warp == 0) prefetch_small_step_inputs(D, ws, it, scr_floats, lane, 32);
 
   // ---- grid ticket: the last CTA to finish runs the small-parameter step ----
-  // every warp's atomics are ordered before the barrier at CTA scope; thread 0's fence then makes them visible at GPU
-  // scope before the ticket (fence cumulativity), so one fence per CTA suffices
   __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    s_flag = (atomicAdd(D.counters, 1) == int(gridDim.x) - 1);
-  }
+  if (tid == 0) s_flag = (grid_ticket(D.counters) == int(gridDim.x) - 1);
   __syncthreads();
   if (dbg && lane == 0) dbg[3] = gtime();
   if (!s_flag) return;
-  __threadfence();
   if (tid == 0) D.counters[0] = 0;   // re-arm for the next launch
-  small_param_step(D, ws, it, s_red);
+  // every stage this CTA issued has been consumed: the ring is idle and serves as the small step's scratch
+  small_step(D, ws, it, s_red, reinterpret_cast<float*>(s_dyn), scr_floats);
   D3R_TSTAMP(5);
 }
 
@@ -483,6 +500,11 @@ static int launch_stream_t(const d3r_align_desc* desc, int it_begin, int it_end,
   cfg.numAttrs = 1;
   for (int it = it_begin; it < it_end; ++it) D3R_CUDA(cudaLaunchKernelEx(&cfg, align_stream_kernel<kL2, PPT, NST>, *desc, it));
   D3R_LAUNCH_CHECK();
+  return D3R_OK;
+}
+
+int stream_set_debug(unsigned long long* p) {   // this translation unit's copy of the timeline pointer
+  D3R_CUDA(cudaMemcpyToSymbol(g_align_dbg, &p, sizeof(p)));
   return D3R_OK;
 }
 

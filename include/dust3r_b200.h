@@ -134,6 +134,12 @@ typedef struct d3r_align_desc {
   int32_t reserved0;
   const void* items;            /* [n_items] d3r_align_item                                            */
   const int32_t* warp_item_ptr; /* [stream_grid * 8 + 1]                                               */
+  /* Optional second traversal of the same items in REVERSE global order (items_rev[k] = items[n_items-1-k],
+   * with its own warp split).  When set, odd iterations walk it: what an iteration streamed last is what
+   * the next one streams first, so the tail of every pass is still resident in the 126 MB L2 (observations
+   * are constants of the problem).  NULL = every iteration walks `items`.                              */
+  const void* items_rev;
+  const int32_t* warp_item_ptr_rev;
 } d3r_align_desc;
 
 /* One work item of the streaming kernel: `nslots` consecutive 64-pixel slots of image `img`. */

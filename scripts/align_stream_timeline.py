@@ -29,7 +29,7 @@ for rep in range(5):
     lib.d3r_align_set_debug(None)
     traw = buf.cpu().numpy().astype(np.float64)
     t = traw[:nw]
-    st = traw[nw:].reshape(-1)[:6]
+    st = traw[nw:].reshape(-1)[:12]
     t0 = t[:, 1].min()          # first warp released from griddepcontrol.wait
     us = lambda x: (x - t0) / 1e3
     entry, rel, done, tick = us(t[:, 0]), us(t[:, 1]), us(t[:, 2]), us(t[:, 3])
