@@ -182,19 +182,25 @@ __global__ void __launch_bounds__(kThreads) attention_kernel(const __nv_bfloat16
   }
 }
 
-static int g_impl = 2;  // 2: tcgen05 split-row kernel (attention_tc2.cu, default), 1: tcgen05 row-per-thread kernel
-                        // (attention_tc.cu), 0: mma.sync streaming kernel (A/B reference)
+static int g_impl = 3;  // 3 (default): tcgen05 split-row kernel with P in TMEM (attention_tc3.cu), 2: tcgen05 split-row kernel with P through
+                        // shared memory (attention_tc2.cu), 1: tcgen05 row-per-thread kernel (attention_tc.cu), 0: mma.sync
+                        // streaming kernel (A/B reference)
 void set_tc2_ablation(int a);
+void set_tc3_ablation(int a);
+int attention_hd64_tc3(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
+                       long long ldo, int B, int heads, int Nq, int Nk, float scale, cudaStream_t st);
 void set_tc_occupancy_pad(int bytes);
 // impl 1 + 10k (debug): k x 16 KB of extra shared memory per CTA
 void set_impl(int impl) {
   g_impl = impl % 10;
   if (g_impl == 1) { set_tc_occupancy_pad((impl / 10) * 16 * 1024); set_tc2_ablation(0); }
+  else if (g_impl == 3) { set_tc_occupancy_pad(0); set_tc3_ablation(impl / 10); }
   else { set_tc_occupancy_pad(0); set_tc2_ablation(impl / 10); }
 }   // impl 12/22/32: timing ablations of impl 2 (debug)
 
 int attention_hd64(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
                    long long ldo, int B, int heads, int Nq, int Nk, float scale, cudaStream_t st) {
+  if (g_impl == 3) return attention_hd64_tc3(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, scale, st);
   if (g_impl == 2) return attention_hd64_tc2(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, scale, st);
   if (g_impl == 1) return attention_hd64_tc(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, scale, st);
   D3R_CHECK_ARG(q && k && v && out && B > 0 && heads > 0 && Nq > 0 && Nk > 0, "attention: bad arguments");

@@ -40,7 +40,7 @@ def _rel(a, b):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize('impl', [0, 1, 2])
+@pytest.mark.parametrize('impl', [0, 1, 2, 3])
 def test_attention_matches_torch(cuda_device, impl):
     from dust3r_b200 import _lib
     lib = _lib.get_lib()
@@ -61,9 +61,45 @@ def test_attention_matches_torch(cuda_device, impl):
         ref = (torch.softmax(qf @ kf.transpose(-1, -2) * 0.125, dim=-1) @ vf).permute(0, 2, 1, 3)
         assert torch.isfinite(out.float()).all()
         err = (out.float() - ref).abs().max().item()
-        lib.d3r_set_attention_impl(2) if err >= 2e-2 else None
+        lib.d3r_set_attention_impl(3) if err >= 2e-2 else None
         assert err < 2e-2, (impl, B, Hh, Nq, Nk, err)
-    lib.d3r_set_attention_impl(2)
+    lib.d3r_set_attention_impl(3)
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize('impl', [2, 3])
+def test_attention_growing_scores_move_the_reference(cuda_device, impl):
+    """Keys whose logits grow along the sequence (by far more than the 2^8 headroom of the lazy exponent reference) force the
+    online softmax to move its reference and rescale O / l several times per row; masked (ragged) last block included."""
+    from dust3r_b200 import _lib
+    lib = _lib.get_lib()
+    lib.d3r_set_attention_impl(impl)
+    g = torch.Generator().manual_seed(1)
+    try:
+        for (B, Hh, Nq, Nk) in [(2, 2, 256, 768), (1, 3, 130, 700)]:
+            q = torch.randn((B, Nq, Hh, 64), generator=g)
+            k = torch.randn((B, Nk, Hh, 64), generator=g)
+            # logits of key n ~ q.k * (1 + 9 n / Nk) + a rising offset along q's own direction
+            ramp = torch.linspace(1.0, 10.0, Nk).view(1, Nk, 1, 1)
+            k = k * ramp + 0.35 * ramp * q.mean(dim=1, keepdim=True)
+            v = torch.randn((B, Nk, Hh, 64), generator=g)
+            q, k, v = [t.to(cuda_device).bfloat16() for t in (q, k, v)]
+            out = torch.full((B, Nq, Hh, 64), float('nan'), dtype=torch.bfloat16, device=cuda_device)
+            ld = Hh * 64
+            _lib.check(lib.d3r_attention_hd64(q.data_ptr(), ld, k.data_ptr(), ld, v.data_ptr(), ld, out.data_ptr(), ld,
+                                              B, Hh, Nq, Nk, 0.125, _lib.stream_ptr()))
+            torch.cuda.synchronize()
+            qf, kf, vf = [t.float().permute(0, 2, 1, 3) for t in (q, k, v)]
+            logits = qf @ kf.transpose(-1, -2) * 0.125
+            # the scenario is only meaningful if row maxima really outgrow the first block's by more than the headroom
+            growth = (logits.max(dim=-1).values - logits[..., :128].max(dim=-1).values) * 1.4427
+            assert float(growth.max()) > 16
+            ref = (torch.softmax(logits, dim=-1) @ vf).permute(0, 2, 1, 3)
+            assert torch.isfinite(out.float()).all()
+            err = (out.float() - ref).abs().max().item()
+            assert err < 3e-2, (impl, B, Hh, Nq, Nk, err)
+    finally:
+        lib.d3r_set_attention_impl(3)
 
 
 @pytest.mark.timeout(900)
