@@ -346,8 +346,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 // q/k/v may be column slices of wider matrices (fused qkv / kv buffers): the map covers the whole matrix that
 // starts at the 16-byte aligned `*_base` pointer, the head column offset is added in the kernel.
 int attention_tc2_set_debug(void* dev_buf);
+int attention_tc3_set_debug(void* dev_buf);
 int attention_set_debug(void* dev_buf) {
   if (int rc = attention_tc2_set_debug(dev_buf)) return rc;
+  if (int rc = attention_tc3_set_debug(dev_buf)) return rc;
   unsigned long long* p = reinterpret_cast<unsigned long long*>(dev_buf);
   D3R_CUDA(cudaMemcpyToSymbol(tc::g_attn_dbg, &p, sizeof(p)));
   return D3R_OK;

@@ -23,6 +23,7 @@
 #include "prof.h"
 #include "attention_tc_common.cuh"
 #include "pdl.cuh"
+#include <type_traits>
 
 namespace d3r {
 namespace attn {
@@ -74,6 +75,10 @@ __device__ __forceinline__ void pair_barrier(int quarter) {
   asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
 }
 
+// optional cycle stamps of one CTA (debug aid): [4 key blocks][16]: slots 0..7 softmax thread (warp 2 lane 0), 8..15 MMA thread
+__device__ unsigned long long* g_attn3_dbg = nullptr;
+#define A3_STAMP(gg, slot) do { if (dbg && (gg) >= 10u && (gg) < 14u) dbg[((gg) - 10u) * 16 + (slot)] = (unsigned long long)clock64(); } while (0)
+
 template <int ABL>   // ABL: timing ablation (debug; results are wrong for ABL != 0): 1 = no exponentials
 __global__ void __launch_bounds__(kThreads, 2)
 attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -102,6 +107,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nq_tiles = (Nq + BQ - 1) / BQ;
   const int nblk = (Nk + BK - 1) / BK;
+  unsigned long long* dbg = (g_attn3_dbg && blockIdx.x == 5 && (threadIdx.x == 64 || threadIdx.x == 32)) ? g_attn3_dbg : nullptr;
   // work item t -> (query tile, head, image); neighbouring CTAs work on the same (image, head) at the same time,
   // so its K / V are fetched from HBM once and then hit in L2
   auto tile_coords = [&](int t, int& q0, int& h, int& b) {
@@ -151,16 +157,16 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
         int q0, h, b;
         tile_coords(t, q0, h, b);
-        ptx::mbar_wait(ptx::smem_u32(q_empty), (it & 1) ^ 1);
+        ptx::mbar_wait_hint(ptx::smem_u32(q_empty), (it & 1) ^ 1);
         ptx::mbar_arrive_expect_tx(ptx::smem_u32(q_full), kTileBytes);
         ptx::tma_load_3d(ptx::smem_u32(s_q), &tmap_q, ptx::smem_u32(q_full), h * D, q0, b);
         for (int j = 0; j < nblk; ++j, ++g) {
           const uint32_t ks = g % kKStages, kph = (g / kKStages) & 1;
           const uint32_t vs = g % kVStages, vph = (g / kVStages) & 1;
-          ptx::mbar_wait(ptx::smem_u32(&k_empty[ks]), kph ^ 1);
+          ptx::mbar_wait_hint(ptx::smem_u32(&k_empty[ks]), kph ^ 1);
           ptx::mbar_arrive_expect_tx(ptx::smem_u32(&k_full[ks]), kKVBytes);
           ptx::tma_load_3d(ptx::smem_u32(s_k + ks * kKVBytes), &tmap_k, ptx::smem_u32(&k_full[ks]), h * D, j * BK, b);
-          ptx::mbar_wait(ptx::smem_u32(&v_empty[vs]), vph ^ 1);
+          ptx::mbar_wait_hint(ptx::smem_u32(&v_empty[vs]), vph ^ 1);
           ptx::mbar_arrive_expect_tx(ptx::smem_u32(&v_full[vs]), kKVBytes);
           ptx::tma_load_3d(ptx::smem_u32(s_v + vs * kKVBytes), &tmap_v, ptx::smem_u32(&v_full[vs]), h * D, j * BK, b);
         }
@@ -175,18 +181,22 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const uint64_t dq = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(s_q));
       auto issue_s = [&](uint32_t g) {   // g: global key-block index of this CTA
         const uint32_t ks = g % kKStages;
-        ptx::mbar_wait(ptx::smem_u32(&k_full[ks]), (g / kKStages) & 1);
-        if (g > 0) ptx::mbar_wait(ptx::smem_u32(s_free), (g - 1) & 1);  // softmax has drained the previous S
+        A3_STAMP(g, 8);
+        ptx::mbar_wait_hint(ptx::smem_u32(&k_full[ks]), (g / kKStages) & 1);
+        A3_STAMP(g, 9);
+        if (g > 0) ptx::mbar_wait_hint(ptx::smem_u32(s_free), (g - 1) & 1);  // softmax has drained the previous S
+        A3_STAMP(g, 10);
         ptx::tc_fence_after();
         const uint64_t dk = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(s_k + ks * kKVBytes));
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) ptx::umma_bf16_ss(d_s, dq + uint64_t(2 * k), dk + uint64_t(2 * k), idesc_s, k ? 1u : 0u);
         ptx::umma_commit(ptx::smem_u32(&k_empty[ks]));
         ptx::umma_commit(ptx::smem_u32(s_ready));
+        A3_STAMP(g, 11);
       };
       uint32_t g0 = 0, it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it, g0 += nblk) {
-        ptx::mbar_wait(ptx::smem_u32(q_full), it & 1);
+        ptx::mbar_wait_hint(ptx::smem_u32(q_full), it & 1);
         issue_s(g0);
         if (nblk == 1) ptx::umma_commit(ptx::smem_u32(q_empty));
         for (int j = 0; j < nblk; ++j) {
@@ -196,9 +206,12 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             if (j + 2 == nblk) ptx::umma_commit(ptx::smem_u32(q_empty));   // last S of the tile: Q may be replaced
           }
           const uint32_t vs = g % kVStages;
-          ptx::mbar_wait(ptx::smem_u32(p_ready), g & 1);
-          ptx::mbar_wait(ptx::smem_u32(&v_full[vs]), (g / kVStages) & 1);
-          if (j == 0 && it > 0) ptx::mbar_wait(ptx::smem_u32(o_free), (it - 1) & 1);   // previous tile's O has been read
+          A3_STAMP(g, 12);
+          ptx::mbar_wait_hint(ptx::smem_u32(p_ready), g & 1);
+          A3_STAMP(g, 13);
+          ptx::mbar_wait_hint(ptx::smem_u32(&v_full[vs]), (g / kVStages) & 1);
+          A3_STAMP(g, 14);
+          if (j == 0 && it > 0) ptx::mbar_wait_hint(ptx::smem_u32(o_free), (it - 1) & 1);   // previous tile's O has been read
           ptx::tc_fence_after();
           const uint32_t pv = ptx::smem_u32(s_v + vs * kKVBytes);
 #pragma unroll
@@ -209,6 +222,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           }
           ptx::umma_commit(ptx::smem_u32(&v_empty[vs]));
           ptx::umma_commit(ptx::smem_u32(o_done));
+          A3_STAMP(g, 15);
         }
       }
     }
@@ -234,8 +248,10 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       for (int j = 0; j < nblk; ++j) {
         const uint32_t g = g0 + j;
         const int nvalid = min(BK, Nk - j * BK) - half * 64;   // valid keys among this warp's 64 (may be <= 0)
+        A3_STAMP(g, 0);
         ptx::mbar_wait(ptx::smem_u32(s_ready), g & 1);
         ptx::tc_fence_after();
+        A3_STAMP(g, 1);
         uint32_t packed[32];
         uint32_t pmax = 0u;            // (+0, +0): running maximum of the bf16 probabilities (positive bf16 order like floats)
         f2 lsum2 = 0ull;               // packed row-sum accumulator (even keys | odd keys)
@@ -243,14 +259,14 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         float ms_blk;
         // p = 2^(s * scale_log2 - ms): exponent pairs from one packed FFMA2, fp32 MUFU exponentials (a bf16 exponent would
         // cost the dominant keys 2-3 % once the lazy reference lets x grow to +8), packed row sums, one pack to bf16
-        auto exp_chunk = [&](const uint32_t* r, int c0, int n, float ms_) {   // n keys starting at key c0 of this warp's 64
+        auto exp_chunk_t = [&](const uint32_t* r, int c0, int n, float ms_, auto masked) {   // n keys from key c0 of this warp's 64
           const f2 sc2 = pk2(scale_log2, scale_log2), nms2 = pk2(-ms_, -ms_);
 #pragma unroll
           for (int i = 0; i < n / 2; ++i) {
             const f2 x = ffma2(pk2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sc2, nms2);
             float x0, x1;
             upk2(x, x0, x1);
-            if (ragged) {   // masked keys contribute p = 0
+            if constexpr (decltype(masked)::value) {   // masked keys contribute p = 0
               if (c0 + 2 * i >= nvalid) x0 = -INFINITY;
               if (c0 + 2 * i + 1 >= nvalid) x1 = -INFINITY;
             }
@@ -261,43 +277,42 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             packed[c0 / 2 + i] = pb;
           }
         };
+        // the ragged (last, partially filled) key block takes its own copy of the loop: folded into one, the compiler
+        // predicates every key of every block (ISETP + FSEL per key: 23 % of all instructions executed)
+        auto exp_chunk = [&](const uint32_t* r, int c0, int n, float ms_) {
+          if (ragged) exp_chunk_t(r, c0, n, ms_, std::true_type{});
+          else exp_chunk_t(r, c0, n, ms_, std::false_type{});
+        };
+        // TMEM reads and exponentials (MUFU) are the two long poles of a block: software pipeline them inside the warp, 16
+        // keys at a time (tcgen05.ld is asynchronous until tcgen05.wait::ld)
+        uint32_t rb[2][16];
+        tmem_ld_32x32b_x16(t_s, rb[0]);
+        ptx::tmem_ld_wait();
         if (j == 0) {
-          // first block: the reference is the row max over BOTH halves, needed before any exponential
-          uint32_t sr[64];
-          ptx::tmem_ld_32x32b_x32(t_s, sr);
-          ptx::tmem_ld_32x32b_x32(t_s + 32, sr + 32);
-          ptx::tmem_ld_wait();
-          // S_j fully read (by this warp) -> after all eight arrivals the MMA warp may overwrite it with S_{j+1}
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive_relaxed(ptx::smem_u32(s_free));   // publishes only completed TMEM loads
+          // first block: both halves of a row must agree on a reference before any exponential.  The maximum over each
+          // half's FIRST 16 keys is enough: whatever the remaining keys add is handled like growth in later blocks (lazy
+          // reference move), and the whole block can run through the same pipelined loop as the others.
           float mx = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 64; ++i)
-            if (i < nvalid) mx = fmaxf(mx, __uint_as_float(sr[i]));
+          for (int i = 0; i < 16; ++i)
+            if (i < nvalid) mx = fmaxf(mx, __uint_as_float(rb[0][i]));
           x_own[2 * 256] = mx;
           pair_barrier(quarter);
           mx = fmaxf(mx, x_peer[2 * 256]);
-          ms = (mx == -INFINITY) ? 0.f : mx * scale_log2;   // -inf cannot happen for Nk >= 1
-          ms_blk = ms;
-          exp_chunk(sr, 0, 64, ms_blk);
-        } else {
-          // TMEM reads (16 B / clk / SM quarter) and exponentials (MUFU) are the two long poles of a block: software
-          // pipeline them inside the warp, 16 keys at a time (tcgen05.ld is asynchronous until tcgen05.wait::ld)
-          ms_blk = ms;
-          uint32_t rb[2][16];
-          tmem_ld_32x32b_x16(t_s, rb[0]);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (c < 3) tmem_ld_32x32b_x16(t_s + 16 * (c + 1), rb[(c + 1) & 1]);
-            exp_chunk(rb[c & 1], 16 * c, 16, ms_blk);
-            if (c < 3) ptx::tmem_ld_wait();
-          }
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive_relaxed(ptx::smem_u32(s_free));   // publishes only completed TMEM loads
+          ms = (mx == -INFINITY) ? 0.f : mx * scale_log2;   // -inf: no valid key among the 2 x 16 (Nk < 16): any reference works
         }
+        ms_blk = ms;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < 3) tmem_ld_32x32b_x16(t_s + 16 * (c + 1), rb[(c + 1) & 1]);
+          exp_chunk(rb[c & 1], 16 * c, 16, ms_blk);
+          if (c < 3) ptx::tmem_ld_wait();
+        }
+        // S_j fully read (by this warp) -> after all eight arrivals the MMA warp may overwrite it with S_{j+1}
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_relaxed(ptx::smem_u32(s_free));   // publishes only completed TMEM loads
+        A3_STAMP(g, 2);
         float rs0, rs1;
         upk2(lsum2, rs0, rs1);
         const float rs = rs0 + rs1;
@@ -307,6 +322,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           ptx::mbar_wait(ptx::smem_u32(o_done), (g - 1) & 1);
           ptx::tc_fence_after();
         }
+        A3_STAMP(g, 3);
         // the partner's maximum of the PREVIOUS block (stored before its p_ready arrival, hence before the o_done
         // just waited for)
         float peer_prev = -INFINITY;
@@ -339,11 +355,14 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         }
         own_prev = __log2f(fmaxf(bf_lo(pmax), bf_hi(pmax))) + ms_blk;   // absolute (log2 domain) block maximum; -inf if masked
         x_own[(j & 1) * 256] = own_prev;
+        A3_STAMP(g, 4);
         tmem_st_wait();
+        A3_STAMP(g, 5);
         // P_j (and a rescaled O) are in TMEM: publish (the release also covers the shared-memory store above)
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(p_ready));
+        A3_STAMP(g, 6);
       }
       // ---- epilogue: O / l -> bf16 -> global (each half: 32 of the 64 columns) ----
       ptx::mbar_wait(ptx::smem_u32(o_done), (g0 + nblk - 1) & 1);
@@ -371,6 +390,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       }
       // the slot-2 exchange cell is reused by the next tile's first-block maximum: both halves must have read it
       pair_barrier(quarter);
+      A3_STAMP(g0 + nblk - 1, 7);
     }
   }
   ptx::tc_fence_before();
@@ -382,6 +402,12 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 }
 
 }  // namespace tc3
+
+int attention_tc3_set_debug(void* dev_buf) {
+  unsigned long long* p = reinterpret_cast<unsigned long long*>(dev_buf);
+  D3R_CUDA(cudaMemcpyToSymbol(tc3::g_attn3_dbg, &p, sizeof(p)));
+  return D3R_OK;
+}
 
 static int g_tc3_ablation = 0;
 void set_tc3_ablation(int a) { g_tc3_ablation = a; }

@@ -5,7 +5,8 @@ import torch
 from dust3r_b200 import _lib
 lib = _lib.get_lib()
 abl = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-lib.d3r_set_attention_impl(2 + 10 * abl)
+impl = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+lib.d3r_set_attention_impl(impl + 10 * abl)
 B, Hh, N = 64, 16, 768
 ld = 3 * Hh * 64
 qkv = torch.randn((B, N, ld), device='cuda').bfloat16()
@@ -22,9 +23,10 @@ f(); torch.cuda.synchronize()
 lib.d3r_attention_set_debug(None)
 d = dbg[:64].cpu().numpy().reshape(4, 16)
 t0 = d[d > 0].min()
-names = ['sm:wait_s', 'sm:got_s', 'sm:exps_done', 'sm:o_done_seen', 'sm:P_stored', 'sm:xchg_done', 'sm:p_arrived', '-',
+names = ['sm:wait_s', 'sm:got_s', 'sm:exps_done', 'sm:o_done_seen', 'sm:P_stored', 'sm:xchg_done', 'sm:p_arrived', 'sm:epilogue_done',   # impl 3: 4 = P st issued, 5 = st complete
+        
          'mma:S_begin', 'mma:k_full', 'mma:s_free', 'mma:S_issued', 'mma:wait_p', 'mma:p_seen', 'mma:v_full', 'mma:PV_issued']
 print('ablation', abl)
 for gi in range(4):
     ev = sorted((int(d[gi, k] - t0), names[k]) for k in range(16) if d[gi, k] > 0)
-    print('block', 6 + gi, ' '.join(f'{n}@{t}' for t, n in ev))
+    print('block', (10 if impl == 3 else 6) + gi, ' '.join(f'{n}@{t}' for t, n in ev))
