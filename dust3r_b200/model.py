@@ -197,15 +197,22 @@ class AsymmetricCroCo3DStereo(nn.Module, _HubMixin, **_hub_kwargs):
             self.repack()
         H, W = int(img1.shape[-2]), int(img1.shape[-1])
         H2, W2 = int(img2.shape[-2]), int(img2.shape[-1])
-        shape1 = view1.get('true_shape', torch.tensor(img1.shape[-2:])[None].repeat(B, 1))
-        shape2 = view2.get('true_shape', torch.tensor(img2.shape[-2:])[None].repeat(B, 1))
+        shape1 = torch.as_tensor(view1.get('true_shape', torch.tensor(img1.shape[-2:])[None].repeat(B, 1))).cpu()
+        shape2 = torch.as_tensor(view2.get('true_shape', torch.tensor(img2.shape[-2:])[None].repeat(B, 1))).cpu()
+        if self.landscape_only:
+            # ManyAR batches (patch_embed.py:32-70 + transpose_to_landscape.wrapper_yes, utils/misc.py:66-95): every image
+            # tensor is stored in landscape; items whose true_shape says portrait are the transposed storage of a portrait image
+            port1, port2 = shape1[:, 0] > shape1[:, 1], shape2[:, 0] > shape2[:, 1]
+            for ts, port, (Hv, Wv) in ((shape1, port1, (H, W)), (shape2, port2, (H2, W2))):
+                assert Wv >= Hv, f'img should be in landscape mode, but got W={Wv} H={Hv}'
+                want = torch.where(port[:, None], torch.tensor([[Wv, Hv]]), torch.tensor([[Hv, Wv]]))
+                assert bool((ts == want).all()), 'true_shape must be the image tensor size (landscape) or its transpose (portrait)'
+            if bool(port1.any()) or bool(port2.any()):
+                return self._forward_many_ar(view1, view2, port1, port2)
         for ts, (Hv, Wv) in ((shape1, (H, W)), (shape2, (H2, W2))):
-            ts = torch.as_tensor(ts)
             assert ts[0:1].allclose(ts), 'true_shape must be all identical'
             h, w = [int(v) for v in ts[0].tolist()]
             if (h, w) != (Hv, Wv):
-                if self.landscape_only and (w, h) == (Hv, Wv):
-                    raise NotImplementedError('portrait images under landscape_only=True (training-time ManyAR path)')
                 raise AssertionError(f'true_shape {(h, w)} does not match the image tensor {(Hv, Wv)}')
         if (H, W) != (H2, W2):
             # model.py:147-151: the two views are encoded separately; the decoder cross-attends between the two grids
@@ -228,6 +235,37 @@ class AsymmetricCroCo3DStereo(nn.Module, _HubMixin, **_hub_kwargs):
         res2['pts3d_in_other_view'] = res2.pop('pts3d')
         return res1, res2
 
+
+    def _forward_many_ar(self, view1, view2, port1, port2):
+        """landscape_only=True with portrait items: the reference embeds a portrait item from its un-transposed pixels
+        (ManyAR_PatchEmbed), runs the head at the portrait size and transposes the result back (wrapper_yes) -- per image
+        that is exactly transpose(model(un-transposed image)).  Items are grouped by the orientation of their two views (at
+        most four groups); each group is an ordinary batch (a landscape/portrait pair is a pair of two image sizes)."""
+        img1, img2 = view1['img'], view2['img']
+        B = img1.shape[0]
+        out1, out2 = {}, {}
+        for p1 in (False, True):
+            for p2 in (False, True):
+                sel = torch.nonzero((port1 == p1) & (port2 == p2)).flatten()
+                if sel.numel() == 0:
+                    continue
+                seld = sel.to(img1.device)
+                a, b = img1.index_select(0, seld), img2.index_select(0, seld)
+                a = a.swapaxes(-1, -2).contiguous() if p1 else a
+                b = b.swapaxes(-1, -2).contiguous() if p2 else b
+                was, self.landscape_only = self.landscape_only, False
+                try:
+                    n = int(sel.numel())   # distinct instance names: no symmetrised-batch shortcut inside a group (same results)
+                    r1, r2 = self.forward(dict(img=a, instance=[f'a{i}' for i in range(n)]), dict(img=b, instance=[f'b{i}' for i in range(n)]))
+                finally:
+                    self.landscape_only = was
+                for res, port, out in ((r1, p1, out1), (r2, p2, out2)):
+                    for k, v in res.items():
+                        v = v.swapaxes(1, 2) if port else v
+                        if k not in out:
+                            out[k] = v.new_empty((B,) + tuple(v.shape[1:]))
+                        out[k].index_copy_(0, seld, v.contiguous())
+        return out1, out2
 
     def forward_indexed(self, imgs, idx1, idx2):
         """Extension used by inference(): `imgs` (n,3,H,W) are the DISTINCT images of a batch (CUDA), pair b is

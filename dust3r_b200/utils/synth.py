@@ -130,3 +130,16 @@ def synth_consistent_scene(n_imgs: int, edges, H: int, W: int, seed: int = 0, no
                pred1=dict(pts3d=torch.stack(p1), conf=torch.stack(c1)),
                pred2=dict(pts3d_in_other_view=torch.stack(p2), conf=torch.stack(c2)), loss=None)
     return out, torch.stack(cams), f
+
+
+def many_ar_inputs(H: int, W: int, seed: int = 9):
+    """4 pairs stored in landscape (H x W, W >= H) for the landscape_only=True (ManyAR) path; orientation of
+    (view1, view2) per item: LL, LP, PL, PP -- a portrait item is the transposed storage of a (W x H) image."""
+    g = torch.Generator().manual_seed(seed)
+    img1 = torch.rand((4, 3, H, W), generator=g) * 2 - 1
+    img2 = torch.rand((4, 3, H, W), generator=g) * 2 - 1
+    L, P = [H, W], [W, H]
+    ts1 = torch.tensor([L, L, P, P], dtype=torch.int32)
+    ts2 = torch.tensor([L, P, L, P], dtype=torch.int32)
+    return (dict(img=img1, true_shape=ts1, instance=['0', '1', '2', '3']),
+            dict(img=img2, true_shape=ts2, instance=['4', '5', '6', '7']))

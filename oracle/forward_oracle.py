@@ -27,13 +27,36 @@ import torch.nn.functional as F
 
 LN_EPS = 1e-6  # croco/models/croco.py:33 (partial(nn.LayerNorm, eps=1e-6))
 
+# Calibration mode (tests only): with OPERAND_DTYPE = torch.bfloat16 every contraction (linear, convolution, Q K^T, P V) sees
+# operands rounded to bf16 and accumulates in fp32 -- what ANY bf16-operand / fp32-accumulate implementation computes up to
+# summation order.  The distance between this and the plain fp32 oracle is the error the product is entitled to; the
+# distance between the product and this mode is what is left for implementation error.  Default None = the reference's fp32.
+OPERAND_DTYPE = None
+
+
+class operand_rounding:
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        global OPERAND_DTYPE
+        self.prev, OPERAND_DTYPE = OPERAND_DTYPE, self.dtype
+
+    def __exit__(self, *a):
+        global OPERAND_DTYPE
+        OPERAND_DTYPE = self.prev
+
+
+def _r(t):
+    return t if OPERAND_DTYPE is None or t is None else t.to(OPERAND_DTYPE).to(torch.float32)
+
 
 def _ln(x, sd, prefix):
     return F.layer_norm(x, (x.shape[-1],), sd[prefix + '.weight'], sd[prefix + '.bias'], LN_EPS)
 
 
 def _lin(x, sd, prefix):
-    return F.linear(x, sd[prefix + '.weight'], sd[prefix + '.bias'])
+    return F.linear(_r(x), _r(sd[prefix + '.weight']), sd[prefix + '.bias'])
 
 
 def positions(B, h, w):
@@ -69,9 +92,9 @@ def rope2d(t, pos, base):
 
 
 def _attention(q, k, v, scale):
-    attn = (q @ k.transpose(-2, -1)) * scale
+    attn = (_r(q) @ _r(k).transpose(-2, -1)) * scale
     attn = attn.softmax(dim=-1)
-    return attn @ v
+    return _r(attn) @ _r(v)
 
 
 def self_attention(x, pos, sd, prefix, nh, base):
@@ -121,7 +144,7 @@ def encode(img, sd, cfg, stages=None):
     B, _, H, W = img.shape
     p = cfg.patch_size
     assert H % p == 0 and W % p == 0
-    x = F.conv2d(img, sd['patch_embed.proj.weight'], sd['patch_embed.proj.bias'], stride=p)
+    x = F.conv2d(_r(img), _r(sd['patch_embed.proj.weight']), sd['patch_embed.proj.bias'], stride=p)
     x = x.flatten(2).transpose(1, 2)
     pos = positions(B, H // p, W // p)
     if stages is not None:
@@ -157,7 +180,7 @@ def decode(f1, pos1, f2, pos2, sd, cfg, stages=None):
 
 
 def _conv(x, sd, prefix, **kw):
-    return F.conv2d(x, sd[prefix + '.weight'], sd.get(prefix + '.bias'), **kw)
+    return F.conv2d(_r(x), _r(sd[prefix + '.weight']), sd.get(prefix + '.bias'), **kw)
 
 
 def _rcu(x, sd, prefix):
@@ -185,9 +208,9 @@ def dpt_head(tokens, H, W, sd, prefix, cfg, stages=None, tag=''):
         layers.append(t.transpose(1, 2).reshape(B, t.shape[2], nh, nw))
     ap = prefix + '.act_postprocess'
     l0 = _conv(layers[0], sd, ap + '.0.0')
-    l0 = F.conv_transpose2d(l0, sd[ap + '.0.1.weight'], sd[ap + '.0.1.bias'], stride=4)
+    l0 = F.conv_transpose2d(_r(l0), _r(sd[ap + '.0.1.weight']), sd[ap + '.0.1.bias'], stride=4)
     l1 = _conv(layers[1], sd, ap + '.1.0')
-    l1 = F.conv_transpose2d(l1, sd[ap + '.1.1.weight'], sd[ap + '.1.1.bias'], stride=2)
+    l1 = F.conv_transpose2d(_r(l1), _r(sd[ap + '.1.1.weight']), sd[ap + '.1.1.bias'], stride=2)
     l2 = _conv(layers[2], sd, ap + '.2.0')
     l3 = _conv(layers[3], sd, ap + '.3.0')
     l3 = _conv(l3, sd, ap + '.3.1', stride=2, padding=1)

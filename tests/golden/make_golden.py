@@ -21,15 +21,15 @@ sys.path.insert(0, '/root/reference')
 sys.path.insert(0, ROOT)
 
 from dust3r_b200.config import ModelConfig, vitl_512_dpt, vitl_224_linear  # noqa: E402
-from dust3r_b200.utils.synth import synth_state_dict, synth_images, synth_pair_predictions  # noqa: E402
+from dust3r_b200.utils.synth import synth_state_dict, synth_images, synth_pair_predictions, many_ar_inputs  # noqa: E402
 
 inf = float('inf')
 
 
-def ref_model(cfg):
+def ref_model(cfg, patch_embed_cls='PatchEmbedDust3R'):
     from dust3r.model import AsymmetricCroCo3DStereo
     m = AsymmetricCroCo3DStereo(
-        pos_embed=cfg.pos_embed, patch_embed_cls='PatchEmbedDust3R', img_size=cfg.img_size, head_type=cfg.head_type,
+        pos_embed=cfg.pos_embed, patch_embed_cls=patch_embed_cls, img_size=cfg.img_size, head_type=cfg.head_type,
         output_mode='pts3d', depth_mode=cfg.depth_mode, conf_mode=cfg.conf_mode, enc_embed_dim=cfg.enc_embed_dim,
         enc_depth=cfg.enc_depth, enc_num_heads=cfg.enc_num_heads, dec_embed_dim=cfg.dec_embed_dim,
         dec_depth=cfg.dec_depth, dec_num_heads=cfg.dec_num_heads, landscape_only=cfg.landscape_only).eval()
@@ -42,6 +42,26 @@ SMALL = dict(
     small_linear=(ModelConfig(img_size=(96, 96), enc_embed_dim=192, enc_depth=3, enc_num_heads=3, dec_embed_dim=128,
                               dec_depth=2, dec_num_heads=2, head_type='linear', landscape_only=False), 80, 64),
 )
+
+
+def many_ar_golden():
+    """landscape_only=True + ManyAR_PatchEmbed (the training-time configuration): transposed portrait items in a landscape
+    batch -> ManyAR_PatchEmbed.forward (patch_embed.py:42-70) and transpose_to_landscape.wrapper_yes (utils/misc.py:66-95)."""
+    for name in ('small_linear', 'small_dpt'):
+        cfg0, H, W = SMALL[name]
+        H, W = min(H, W), max(H, W)
+        cfg = copy.deepcopy(cfg0)
+        cfg.landscape_only = True
+        m = ref_model(cfg, patch_embed_cls='ManyAR_PatchEmbed')
+        sd = synth_state_dict(cfg, seed=11)
+        m.load_state_dict(sd, strict=True)
+        v1, v2 = many_ar_inputs(H, W)
+        with torch.no_grad():
+            r1, r2 = m(v1, v2)
+        np.savez_compressed(os.path.join(HERE, f'forward_{name}_manyar.npz'), H=H, W=W,
+                            pts3d=r1['pts3d'].numpy(), conf1=r1['conf'].numpy(),
+                            pts3d_in_other_view=r2['pts3d_in_other_view'].numpy(), conf2=r2['conf'].numpy())
+        print('wrote many-AR', name, r1['pts3d'].shape)
 
 
 def forward_goldens():
@@ -62,6 +82,8 @@ def forward_goldens():
                             idx1=np.int64(out['view1']['idx']), idx2=np.int64(out['view2']['idx']),
                             img_sum=np.float64([float(i['img'].double().sum()) for i in imgs]))
         print('wrote', name, out['pred1']['pts3d'].shape)
+
+    many_ar_golden()
 
     # the two published architectures, one 1-pair batch each, strided sample of the outputs
     for name, cfg, H, W, stride in (('vitl_512_dpt', vitl_512_dpt(), 384, 512, 8), ('vitl_224_linear', vitl_224_linear(), 224, 224, 4)):

@@ -251,3 +251,74 @@ def test_published_architectures_match_reference_golden(cuda_device, name):
         got = got[:, ::s, ::s]
         assert torch.isfinite(got).all()
         assert _rel(got, ref) < 4e-2, (key, _rel(got, ref))
+
+
+@pytest.mark.timeout(1800)
+def test_batched_forward_path_matches_oracle_and_error_is_operand_rounding(cuda_device):
+    """The benchmark's code path: packed.forward on B = 16 distinct 512x384 pairs of the published ViT-L / ViT-B / DPT
+    architecture (pair-GEMM policy, multi-tile persistent attention, M = 24576 / 49152 token GEMMs), compared per pair with the
+    CPU oracle on three of the pairs (first, middle, last: a pair's result must not depend on its batch).
+
+    Tolerance calibration: the oracle is evaluated twice -- in the reference's fp32, and with every
+    contraction's operands rounded to bf16 (fp32 accumulation), i.e. what any bf16-operand implementation computes.  The
+    product must sit much closer to the second than the second sits to the first: the measured 1e-2 distance to the fp32
+    reference is operand rounding, not implementation error."""
+    import oracle.forward_oracle as fo
+    from dust3r_b200.config import vitl_512_dpt
+    cfg, H, W = vitl_512_dpt(), 384, 512
+    net, sd = _build(cfg, 0, cuda_device)
+    B = 16
+    g = torch.Generator().manual_seed(77)
+    imgs = torch.rand((2 * B, 3, H, W), generator=g) * 2 - 1
+    packed = net.repack()
+    idx1, idx2 = np.arange(B, dtype=np.int32), B + np.arange(B, dtype=np.int32)
+    r1, r2 = packed.forward(imgs.to(cuda_device), idx1, idx2, B, H, W)
+    torch.cuda.synchronize()
+    assert torch.isfinite(r1['pts3d']).all() and torch.isfinite(r2['conf']).all()
+    worst = dict(fp32=0.0, bf16=0.0, floor=0.0)
+    for k in (0, B // 2, B - 1):
+        a, b = imgs[k:k + 1], imgs[B + k:B + k + 1]
+        o1, o2 = fo.forward_oracle(sd, cfg, a, b)
+        with fo.operand_rounding(torch.bfloat16):
+            e1, e2 = fo.forward_oracle(sd, cfg, a, b)
+        for got, ref, emu in ((r1['pts3d'][k], o1['pts3d'][0], e1['pts3d'][0]), (r1['conf'][k], o1['conf'][0], e1['conf'][0]),
+                              (r2['pts3d'][k], o2['pts3d_in_other_view'][0], e2['pts3d_in_other_view'][0]),
+                              (r2['conf'][k], o2['conf'][0], e2['conf'][0])):
+            got = got.cpu()
+            worst['fp32'] = max(worst['fp32'], _rel(got, ref))
+            worst['bf16'] = max(worst['bf16'], _rel(got, emu))
+            worst['floor'] = max(worst['floor'], _rel(emu, ref))
+        # per-pixel bound on the pointmap: 99.9 % of the pixels within 5 % of the scene scale (median point norm)
+        d = (r1['pts3d'][k].cpu() - o1['pts3d'][0]).norm(dim=-1)
+        scale = o1['pts3d'][0].norm(dim=-1).median()
+        assert float(torch.quantile(d.flatten()[::7], 0.999)) < 0.05 * float(scale), (k, float(d.max()), float(scale))
+    print('batched forward vs oracle: rel-L2 to fp32 oracle %.3e, to bf16-operand oracle %.3e; bf16-operand oracle vs fp32 oracle %.3e'
+          % (worst['fp32'], worst['bf16'], worst['floor']))
+    assert worst['fp32'] < 3e-2, worst
+    assert worst['bf16'] < 0.6 * max(worst['floor'], 1e-3) + 2e-3, worst
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize('name', ['small_linear', 'small_dpt'])
+def test_landscape_only_many_ar_batch_matches_reference_golden(cuda_device, name):
+    """landscape_only=True with transposed portrait items in the batch (ManyAR_PatchEmbed, patch_embed.py:42-70, and
+    transpose_to_landscape.wrapper_yes, utils/misc.py:66-95): all four orientation combinations of a pair in one batch,
+    against the output of the unmodified reference in that configuration."""
+    import copy
+    from dust3r_b200.utils.synth import many_ar_inputs
+    cfg0, _, _ = _small_cfgs()[name]
+    cfg = copy.deepcopy(cfg0)
+    cfg.landscape_only = True
+    net, sd = _build(cfg, 11, cuda_device)
+    assert net.landscape_only
+    gold = np.load(os.path.join(GOLDEN, f'forward_{name}_manyar.npz'))
+    H, W = int(gold['H']), int(gold['W'])
+    v1, v2 = many_ar_inputs(H, W)
+    v1 = dict(v1, img=v1['img'].to(cuda_device))
+    v2 = dict(v2, img=v2['img'].to(cuda_device))
+    r1, r2 = net(v1, v2)
+    for got, key in ((r1['pts3d'], 'pts3d'), (r1['conf'], 'conf1'), (r2['pts3d_in_other_view'], 'pts3d_in_other_view'), (r2['conf'], 'conf2')):
+        ref = torch.from_numpy(gold[key])
+        assert got.shape == ref.shape
+        for k in range(4):
+            assert _rel(got[k].cpu(), ref[k]) < 3e-2, (name, key, k, _rel(got[k].cpu(), ref[k]))

@@ -146,3 +146,26 @@ def test_forward_oracle_bit_matches_live_reference():
     assert torch.allclose(r1['conf'], o1['conf'], rtol=1e-5, atol=1e-6)
     assert torch.allclose(r2['pts3d_in_other_view'], o2['pts3d_in_other_view'], rtol=1e-5, atol=1e-6)
     assert torch.allclose(r2['conf'], o2['conf'], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('name', ['small_linear', 'small_dpt'])
+def test_many_ar_golden_equals_oracle_on_untransposed_items(name):
+    """landscape_only=True (ManyAR_PatchEmbed + transpose_to_landscape.wrapper_yes, utils/misc.py:66-95): for a portrait item
+    stored transposed in a landscape batch the reference returns transpose(model(un-transposed image)).  Checked item by item
+    against the oracle on the golden produced by the unmodified reference (tests/golden/make_golden.py::many_ar_golden)."""
+    gold = np.load(os.path.join(GOLDEN, f'forward_{name}_manyar.npz'))
+    H, W = int(gold['H']), int(gold['W'])
+    from dust3r_b200.utils.synth import many_ar_inputs
+    v1, v2 = many_ar_inputs(H, W)
+    cfg = _small_cfgs()[name][0]
+    sd = synth_state_dict(cfg, seed=11)
+    for k in range(4):
+        p1, p2 = bool(v1['true_shape'][k, 0] > v1['true_shape'][k, 1]), bool(v2['true_shape'][k, 0] > v2['true_shape'][k, 1])
+        a, b = v1['img'][k:k + 1], v2['img'][k:k + 1]
+        o1, o2 = forward_oracle(sd, cfg, a.swapaxes(-1, -2) if p1 else a, b.swapaxes(-1, -2) if p2 else b)
+        for got, port, key in ((o1['pts3d'], p1, 'pts3d'), (o1['conf'], p1, 'conf1'),
+                               (o2['pts3d_in_other_view'], p2, 'pts3d_in_other_view'), (o2['conf'], p2, 'conf2')):
+            got = got.swapaxes(1, 2) if port else got
+            ref = torch.from_numpy(gold[key][k:k + 1])
+            assert got.shape == ref.shape
+            assert float((got - ref).abs().max()) <= 2e-5 * float(ref.abs().max()), (name, k, key)
