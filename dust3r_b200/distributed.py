@@ -74,7 +74,8 @@ class PairOutputGather:
         off = 0
         for which, key, w, _ in self.cols:
             if w and preds[which] is not None:
-                t = preds[which][key]
+                # the fused forward names view 2's pointmap 'pts3d' until model.forward() renames it (model.py:199-211)
+                t = preds[which][key] if key in preds[which] else preds[which]['pts3d']
                 send[:t.shape[0], off:off + w].copy_(t.reshape(t.shape[0], w), non_blocking=True)
             off += w
         # ---- the one collective of the path ----
@@ -100,13 +101,15 @@ class PairOutputGather:
 
 
 @torch.no_grad()
-def inference_sharded(pairs, model, device, batch_size=8, verbose=False, group=None, gather_device=None):
+def inference_sharded(pairs, model, device, batch_size=8, verbose=False, group=None, gather_device=None, return_images=True):
     """inference() over this rank's slice of `pairs` + ONE all-gather -> the full result dict on every rank.
 
     Same return structure as inference(); tensors live on `gather_device` (default: CPU like the reference;
     pass the CUDA device to keep them resident for global_aligner -- they are then views of the gathered
     buffer).  All pairs must share one image size per view (what make_pairs over load_images(size=...) yields;
-    mixed sizes make inference() return lists, which have no packed row layout)."""
+    mixed sizes make inference() return lists, which have no packed row layout).  return_images=False leaves the collated
+    'img' tensors out of view1 / view2 (2.4 MB per view and pair at 512x384 of pure host copying; the aligner only uses them
+    for colours)."""
     if not (dist.is_available() and dist.is_initialized()):
         return inference(pairs, model, device, batch_size=batch_size, verbose=verbose)
     if len(pairs) == 0:
@@ -115,7 +118,8 @@ def inference_sharded(pairs, model, device, batch_size=8, verbose=False, group=N
         raise ValueError('inference_sharded needs all pairs to share one image size per view (run mixed-size pair lists through inference())')
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     lo, hi = shard_bounds(len(pairs), world, rank)
-    local = inference(pairs[lo:hi], model, device, batch_size=batch_size, verbose=verbose, keep_on_device=True) if hi > lo else None
+    local = inference(pairs[lo:hi], model, device, batch_size=batch_size, verbose=verbose, keep_on_device=True,
+                      return_images=False) if hi > lo else None
     backend = dist.get_backend(group)
     comm_dev = torch.device(device) if backend == 'nccl' else torch.device('cpu')
     # shapes come from each view's own images, so a rank without pairs builds the same row layout as the others
@@ -130,8 +134,9 @@ def inference_sharded(pairs, model, device, batch_size=8, verbose=False, group=N
         p1 = {key: v.to(out_dev) for key, v in p1.items()}
         p2 = {key: v.to(out_dev) for key, v in p2.items()}
     # the views (images, indices) are inputs every rank already holds: rebuild them locally in global order
-    view1 = collate_with_cat([a for a, b in pairs])
-    view2 = collate_with_cat([b for a, b in pairs])
+    drop = (lambda v: v) if return_images else (lambda v: {k: x for k, x in v.items() if k != 'img'})
+    view1 = collate_with_cat([drop(a) for a, b in pairs])
+    view2 = collate_with_cat([drop(b) for a, b in pairs])
     return dict(view1=view1, view2=view2, pred1=p1, pred2=p2, loss=None)
 
 

@@ -105,10 +105,11 @@ def _micro_batch(batch_size):
 
 
 @torch.no_grad()
-def inference(pairs, model, device, batch_size=8, verbose=True, keep_on_device=False):
+def inference(pairs, model, device, batch_size=8, verbose=True, keep_on_device=False, return_images=True):
     """inference.py:55-72.  Returns {'view1','view2','pred1','pred2','loss'}; tensors on CPU (pinned) unless
     keep_on_device.  Software pipeline over micro-batches: images are gathered into pinned host memory (which is
-    also the returned, collated view), uploaded on a copy stream, run through one fused forward call, and the
+    also the returned, collated view; return_images=False -- extension -- leaves 'img' out of the returned views and skips
+    that copy where the upload does not need it), uploaded on a copy stream, run through one fused forward call, and the
     predictions are copied D2H on a second side stream into the final (whole pair list) pinned output -- the
     upload of batch k+1 and the download of batch k-1 overlap the compute of batch k."""
     if verbose:
@@ -133,7 +134,7 @@ def inference(pairs, model, device, batch_size=8, verbose=True, keep_on_device=F
     assert rows[0] == rows[1], 'both views of a pair must hold the same number of images'
     proto = [vs[0]['img'] for vs in views]
     # pinned staging = the collated 'img' of the returned views; device copies of the whole pair list (a few MB / pair)
-    img_pin = [torch.empty((rows[k],) + tuple(proto[k].shape[1:]), dtype=proto[k].dtype, pin_memory=True) for k in range(2)]
+    img_pin = None    # allocated below, unless the caller does not want the images back and the upload does not stage through it
     img_dev = None    # device copies of both views: only the non-deduplicated path needs them (allocated there)
     meta_all = [{key: collate_with_cat([v[key] for v in vs]) for key in vs[0] if key != 'img'} for vs in views]
     _mark('alloc+meta')
@@ -173,6 +174,9 @@ def inference(pairs, model, device, batch_size=8, verbose=True, keep_on_device=F
             ev_uniq = torch.cuda.Event()
             ev_uniq.record(up)
             main.wait_event(ev_uniq)
+    all_pinned = all(v['img'].is_pinned() for vs in views for v in vs)
+    if return_images or not (uniq_dev is not None or all_pinned):
+        img_pin = [torch.empty((rows[k],) + tuple(proto[k].shape[1:]), dtype=proto[k].dtype, pin_memory=True) for k in range(2)]
     for i in tqdm.trange(0, n, mb, disable=not verbose):
         chunk = (views[0][i:i + mb], views[1][i:i + mb])
         r1 = r0
@@ -182,6 +186,9 @@ def inference(pairs, model, device, batch_size=8, verbose=True, keep_on_device=F
         for k in range(2):
             # sources already in pinned memory are uploaded straight from where they are; the collated copy that the
             # caller gets back is then filled in the background, off the critical path
+            if img_pin is None:
+                r1 = r0 + sum(int(t.shape[0]) for t in srcs[k])
+                continue
             r1, futs = _fill_pinned(img_pin[k], srcs[k], r0, wait=not (direct or indexed))
             pending.extend(futs)
         _mark('fill')
@@ -193,24 +200,37 @@ def inference(pairs, model, device, batch_size=8, verbose=True, keep_on_device=F
             _mark('h2d+meta')
             pred1, pred2 = model.forward_indexed(sel, [loc[g] for g in g1], [loc[g] for g in g2])
         else:
+            # device staging: two micro-batch sized buffers per view, used alternately (the reference holds one batch on the
+            # GPU at a time; a whole-pair-list copy would grow by 4.7 MB per pair at 512x384).  A buffer is reused two
+            # micro-batches later: the upload stream first waits for the forward that last read it.
             if img_dev is None:
-                img_dev = [torch.empty(img_pin[k].shape, dtype=img_pin[k].dtype, device=dev) for k in range(2)]
+                per_item = [int(v['img'].shape[0]) for v in views[0]]
+                cap = max(sum(per_item[c:c + mb]) for c in range(0, n, mb))
+                img_dev = [[torch.empty((cap,) + tuple(proto[k].shape[1:]), dtype=proto[k].dtype, device=dev) for k in range(2)]
+                           for _ in range(2)]
+                dev_free = [None, None]
+            slot = (i // mb) & 1
+            nrow = r1 - r0
             with torch.cuda.stream(up):
+                if dev_free[slot] is not None:
+                    up.wait_event(dev_free[slot])
                 for k in range(2):
                     if direct:
-                        r = r0
+                        r = 0
                         for t in srcs[k]:
-                            img_dev[k][r:r + int(t.shape[0])].copy_(t, non_blocking=True)
+                            img_dev[slot][k][r:r + int(t.shape[0])].copy_(t, non_blocking=True)
                             r += int(t.shape[0])
                     else:
-                        img_dev[k][r0:r1].copy_(img_pin[k][r0:r1], non_blocking=True)
+                        img_dev[slot][k][:nrow].copy_(img_pin[k][r0:r1], non_blocking=True)
             ev_up = torch.cuda.Event()
             ev_up.record(up)
             main.wait_event(ev_up)
             d = [dict({key: collate_with_cat([v[key] for v in chunk[k]]) for key in chunk[k][0] if key != 'img'},
-                      img=img_dev[k][r0:r1]) for k in range(2)]
+                      img=img_dev[slot][k][:nrow]) for k in range(2)]
             _mark('h2d+meta')
             pred1, pred2 = model(d[0], d[1])
+            dev_free[slot] = torch.cuda.Event()
+            dev_free[slot].record(main)
         _mark('forward-enqueued')
         flat = {('pred1', k): v for k, v in pred1.items()}
         flat.update({('pred2', k): v for k, v in pred2.items()})
@@ -233,7 +253,10 @@ def inference(pairs, model, device, batch_size=8, verbose=True, keep_on_device=F
         f.result()
     _mark('synced')
     main.wait_stream(up)
-    res = dict(view1=dict(meta_all[0], img=img_pin[0]), view2=dict(meta_all[1], img=img_pin[1]), pred1={}, pred2={}, loss=None)
+    if return_images:
+        res = dict(view1=dict(meta_all[0], img=img_pin[0]), view2=dict(meta_all[1], img=img_pin[1]), pred1={}, pred2={}, loss=None)
+    else:
+        res = dict(view1=dict(meta_all[0]), view2=dict(meta_all[1]), pred1={}, pred2={}, loss=None)
     for (which, k), t in outs.items():
         res[which][k] = t
     return res
