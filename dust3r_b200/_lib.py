@@ -70,6 +70,14 @@ def _declare(lib):
     lib.d3r_align_pack_obs.argtypes = [vp, vp, vp, i64, i64, vp]
     lib.d3r_align_pack_entries.restype = C.c_int
     lib.d3r_align_pack_entries.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+    lib.d3r_clean_pointcloud.restype = C.c_int
+    lib.d3r_clean_pointcloud.argtypes = [i32, vp, vp, i32, vp, vp, vp, vp, vp, f32, f32, vp]
+    lib.d3r_procrustes_moments.restype = C.c_int
+    lib.d3r_procrustes_moments.argtypes = [i32, i32, vp, vp, vp, vp, vp]
+    lib.d3r_weiszfeld_focal.restype = C.c_int
+    lib.d3r_weiszfeld_focal.argtypes = [i32, i32, i32, vp, vp, i32, vp, vp]
+    lib.d3r_nearest_neighbours.restype = C.c_int
+    lib.d3r_nearest_neighbours.argtypes = [i32, i32, vp, vp, vp, vp]
     for name in ('d3r_sizeof_align_item', 'd3r_sizeof_pack_entry', 'd3r_align_stream_slots_per_item',
                  'd3r_align_stream_warps_per_cta', 'd3r_align_stream_max_window'):
         getattr(lib, name).restype = C.c_int

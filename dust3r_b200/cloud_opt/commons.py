@@ -125,6 +125,9 @@ def rigid_points_registration(x, y, weights=None, compute_scaling=False):
     """Weighted Kabsch / Umeyama: argmin sum_k w_k |s R x_k + t - y_k|^2  -> (R, t[, s])."""
     if weights is None:
         weights = torch.ones(x.shape[:-1], dtype=x.dtype, device=x.device)
+    if x.is_cuda and x.ndim in (2, 3) and x.shape[-1] == 3:
+        from .scene_ops import rigid_registration                 # moments in one kernel launch (csrc/scene_ops.cu)
+        return rigid_registration(x, y, weights, compute_scaling=compute_scaling)
     w = weights[..., None]
     wsum = w.sum(dim=-2, keepdim=True)
     xm = (w * x).sum(dim=-2, keepdim=True) / wsum

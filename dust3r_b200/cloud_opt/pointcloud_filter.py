@@ -1,7 +1,8 @@
 """Cross-view consistency filter applied after alignment (`clean_pointcloud`, dust3r/cloud_opt/base_opt.py:369-405;
 SURVEY §8f rank 3).  A 3-D point of image i that projects into image j IN FRONT of the surface image j sees there
 (closer than (1 - tol) x j's depth) contradicts j; if j is the more confident of the two at that pixel, i's
-confidence is cut to `bad_conf`.  Plain torch on whatever device the scene lives on: O(n^2 P) projections."""
+confidence is cut to `bad_conf`.  O(n^2 P) projections: CUDA kernel (csrc/scene_ops.cu) for scenes on the GPU, plain torch
+for CPU tensors."""
 from __future__ import annotations
 
 import torch
@@ -32,6 +33,9 @@ def clean_pointcloud(im_confs, K, cams, depthmaps, all_pts3d, tol=0.001, bad_con
     n = len(im_confs)
     assert n == len(cams) == len(K) == len(depthmaps) == len(all_pts3d)
     assert 0 <= tol < 1
+    if n > 0 and all(torch.is_tensor(c) and c.is_cuda for c in im_confs):
+        from .scene_ops import clean_pointcloud as clean_cuda      # one thread per pixel, n launches (csrc/scene_ops.cu)
+        return clean_cuda(im_confs, K, cams, depthmaps, all_pts3d, tol=tol, bad_conf=bad_conf)
     conf = [c.clone() for c in im_confs]
     points = [p.view(*c.shape, 3) for p, c in zip(all_pts3d, im_confs)]
     depth = [d.view(*c.shape) for d, c in zip(depthmaps, im_confs)]

@@ -44,7 +44,11 @@ def estimate_focal_knowing_depth(pts3d, pp, focal_mode='median', min_focal=0., m
         with torch.no_grad():
             focal = _vote_focal(centered_px, pts)
     elif focal_mode == 'weiszfeld':
-        focal = _irls_focal(centered_px, pts)
+        if pts3d.is_cuda:
+            from .cloud_opt.scene_ops import weiszfeld_focal       # one CTA per pointmap (csrc/scene_ops.cu)
+            focal = weiszfeld_focal(pts3d, pp.reshape(-1, 2).expand(B, 2))
+        else:
+            focal = _irls_focal(centered_px, pts)
     else:
         raise ValueError(f'bad {focal_mode=}')
     fov60 = max(H, W) / (2 * math.tan(math.radians(60) / 2))

@@ -111,3 +111,26 @@ def depthmap_to_absolute_camera_coordinates(depthmap, camera_intrinsics, camera_
         R, t = camera_pose[:3, :3], camera_pose[:3, 3]
         X_world = np.einsum("ik, vuk -> vui", R, X_cam) + t[None, None, :]
     return X_world, valid
+
+
+def find_reciprocal_matches(P1, P2):
+    """dust3r/utils/geometry.py:345-361: (reciprocal_in_P2 bool[len(P2)], nn2_in_P1 int[len(P2)], number of matches).
+    P2[k] is a reciprocal match when the nearest point of P1 to it, nn2_in_P1[k], has P2[k] as ITS nearest point in P2.
+    CUDA tensors (N,3) / (M,3) are matched by a brute-force kernel on the GPU (csrc/scene_ops.cu) and returned as tensors;
+    arrays / CPU tensors use scipy's cKDTree exactly like the reference and return numpy."""
+    if torch.is_tensor(P1) and P1.is_cuda:
+        from ..cloud_opt.scene_ops import nearest_neighbours
+        P2 = torch.as_tensor(P2, device=P1.device)
+        nn1_in_P2 = nearest_neighbours(P1, P2)
+        nn2_in_P1 = nearest_neighbours(P2, P1)
+        reciprocal_in_P2 = nn1_in_P2[nn2_in_P1] == torch.arange(len(nn2_in_P1), device=P1.device)
+        return reciprocal_in_P2, nn2_in_P1, int(reciprocal_in_P2.sum())
+    from scipy.spatial import cKDTree
+
+    def nearest(src, dst):
+        return cKDTree(dst).query(src, workers=8)[1]
+    P1, P2 = np.asarray(P1), np.asarray(P2)
+    to_p2, to_p1 = nearest(P1, P2), nearest(P2, P1)
+    mutual_2 = to_p2[to_p1] == np.arange(len(to_p1))
+    assert (to_p1[to_p2] == np.arange(len(to_p2))).sum() == mutual_2.sum()     # the relation is symmetric
+    return mutual_2, to_p1, mutual_2.sum()

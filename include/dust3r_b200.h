@@ -253,8 +253,33 @@ void d3r_set_gemm_pair_min_kblocks(int32_t kblocks);
 int d3r_attention_set_debug(void* dev_buf);
 
 /* Selects the attention kernel: 0 = mma.sync streaming kernel, 1 = tcgen05/TMEM kernel (one thread per query row,
- * 64-key blocks, 3 CTAs/SM), 2 (default) = tcgen05/TMEM split-row kernel (two warps per 32 rows, 128-key blocks). */
+ * 64-key blocks, 3 CTAs/SM), 2 = tcgen05/TMEM split-row kernel (two warps per 32 rows, 128-key blocks, P through shared
+ * memory), 3 (default) = the same with P kept in tensor memory (A-from-TMEM tcgen05.mma). */
 void d3r_set_attention_impl(int32_t impl);
+
+/* ------------------------------------------------------------------------------------------
+ * Scene-level operators either side of the alignment loop.  Device pointers, fp32.
+ * ------------------------------------------------------------------------------------------ */
+/* clean_pointcloud (dust3r/cloud_opt/base_opt.py:369-405): conf[i][p] is cut to bad_conf when image i's world point p lands
+ * in image j in front of j's surface ((1 - tol) * depth_j) where j is more confident; (i, j) visited in the reference's order
+ * (later tests see earlier cuts).  Images are packed back to back: image i = rows [off[i], off[i] + hw[2i] * hw[2i+1]) of
+ * pts3d [.][3] (world frame), conf (updated in place) and depth.  K: [n][3][3], cams: [n][4][4] world-to-camera, row-major. */
+int d3r_clean_pointcloud(int32_t n_imgs, const int32_t* hw_dev, const int64_t* off_dev, int32_t max_area, const float* pts3d_dev,
+                         float* conf_dev, const float* depth_dev, const float* K_dev, const float* cams_dev, float tol,
+                         float bad_conf, void* stream);
+/* Moments of the weighted Umeyama / Kabsch problems roma.rigid_points_registration solves for
+ * dust3r/cloud_opt/init_im_poses.py:66-110, 253-262: per problem b, out[b][17] (fp64) =
+ * { sum w | sum w x (3) | sum w y (3) | sum w y x^T (9, row-major) | sum w |x|^2 } over the n_points rows of x, y [B][P][3], w [B][P]. */
+int d3r_procrustes_moments(int32_t n_problems, int32_t n_points, const float* x_dev, const float* y_dev, const float* w_dev,
+                           double* out_dev, void* stream);
+/* estimate_focal_knowing_depth(..., focal_mode='weiszfeld') (dust3r/post_process.py:12-60) without its final clipping:
+ * pts3d [B][H][W][3] in the camera frame, pp [B][2] -> focal [B] after `steps` re-weighted iterations. */
+int d3r_weiszfeld_focal(int32_t n_maps, int32_t H, int32_t W, const float* pts3d_dev, const float* pp_dev, int32_t steps,
+                        float* focal_dev, void* stream);
+/* Index of the nearest of `points` [M][3] for every row of `queries` [N][3] (squared Euclidean distance, lowest index on a
+ * tie): the two tree queries of find_reciprocal_matches (dust3r/utils/geometry.py:345-361), brute force on the GPU. */
+int d3r_nearest_neighbours(int32_t n_queries, int32_t n_points, const float* queries_dev, const float* points_dev, int32_t* nn_dev,
+                           void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Path 1 — pairwise forward: replaces AsymmetricCroCo3DStereo.forward (dust3r/model.py:199-211 =

@@ -188,3 +188,21 @@ def test_stream_work_items_cover_every_slot_once_and_balance():
             cost.append(sum(int(i['nslots']) * (int(i['deg']) + 3) for i in its))
         busy = [c for c in cost if c > 0]
         assert max(busy) - min(busy) <= 2 * (max(deg) + 3), (max(busy), min(busy))
+
+
+def test_find_reciprocal_matches_host_path_matches_live_reference():
+    """utils/geometry.py:345-361 (scipy cKDTree on the CPU, like the reference); the CUDA path is checked against this one in
+    tests/test_scene_ops_gpu.py."""
+    import numpy as np
+    from conftest import has_reference
+    if not has_reference():
+        pytest.skip('reference not mounted')
+    import sys
+    sys.path.insert(0, '/root/reference')
+    from dust3r.utils.geometry import find_reciprocal_matches as ref
+    from dust3r_b200.utils.geometry import find_reciprocal_matches as mine
+    rng = np.random.default_rng(0)
+    P1 = rng.standard_normal((700, 3)).astype(np.float32)
+    P2 = np.concatenate((P1[:400] + 0.01 * rng.standard_normal((400, 3)).astype(np.float32), rng.standard_normal((150, 3)).astype(np.float32)))
+    a, b = ref(P1, P2), mine(P1, P2)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and int(a[2]) == int(b[2]) > 300
