@@ -195,6 +195,51 @@ def cloud_opt_section(device, pk, steps_iters=300):
                          final_loss=loss))
 
 
+def cloud_opt_config5_section(device, pk, n=50, niter=300):
+    """Alignment leg of BASELINE configs[4] on ONE GPU (alignment does not shard: replicas only): 50 views -> 1225 pairs at
+    512x384, predictions synthesised in HBM (where the all-gather of the sharded forward leaves them), global_aligner in
+    ModularPointCloudOptimizer mode, 300 iterations.  7.9 GB of algorithmic traffic per iteration: no cache effects."""
+    from dust3r_b200.cloud_opt import global_aligner, GlobalAlignerMode
+    edges = [(i, j) for i in range(n) for j in range(i)]
+    g = torch.Generator(device=device).manual_seed(0)
+    E = len(edges)
+    off = torch.tensor([0.0, 0.0, 3.0], device=device)
+    ts = torch.from_numpy(np.int32([[H, W]] * E))
+    mk = lambda: torch.randn((E, H, W, 3), generator=g, device=device) + off
+    cf = lambda: 1 + 5 * torch.rand((E, H, W), generator=g, device=device)
+    out = dict(view1=dict(idx=[int(i) for i, j in edges], instance=[str(i) for i, j in edges], true_shape=ts),
+               view2=dict(idx=[int(j) for i, j in edges], instance=[str(j) for i, j in edges], true_shape=ts),
+               pred1=dict(pts3d=mk(), conf=cf()), pred2=dict(pts3d_in_other_view=mk(), conf=cf()), loss=None)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    torch.manual_seed(0)
+    net = global_aligner(out, device, mode=GlobalAlignerMode.ModularPointCloudOptimizer, verbose=False)
+    eng = net._get_engine()
+    net._engine_push(eng)
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t0
+    eng.run(60)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    losses = eng.run(niter)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    by = eng.algorithmic_bytes_per_iter()
+    gbs = by / (ms / niter) / 1e6
+    res = dict(metric='cloud_opt iters/sec', value=niter / ms * 1e3, unit='iters/s', ms_per_iter=ms / niter, kernel=eng.kernel,
+               config=dict(workload=f'{n} synthetic views -> {E} pairs (symmetrize=False) at 512x384, ModularPointCloudOptimizer, '
+                                    f'{niter} iters, lr 0.01 cosine, dist l1, conf log, init=None; predictions resident in HBM'),
+               aligner_build_s=round(t_build, 3), loss_first=float(losses[0]), loss_last=float(losses[-1]),
+               mem_GB=round(torch.cuda.max_memory_allocated() / 1e9, 1),
+               roofline=dict(bound='hbm', achieved=gbs, peak=pk['hbm'], unit='GB/s', frac=gbs / pk['hbm'], traffic=None,
+                             algorithmic_bytes_per_iter=by, peak_source=pk['source']))
+    del net, eng, out
+    torch.cuda.empty_cache()
+    return res
+
+
 def _oracle_forward_setup(threads):
     from dust3r_b200.config import vitl_512_dpt
     from dust3r_b200.utils.synth import synth_state_dict, synth_images
@@ -446,7 +491,21 @@ def main():
         h2d = 2 * B * 3 * H * W * 4
         d2h = 2 * B * H * W * 4 * 4   # pts3d (3 f32) + conf (1 f32) for both views; the returned views are the host originals
         e2e = dict(value=world * B * n_e2e / float(dt[0]), unit='image-pairs/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                   api='dust3r_b200.inference.inference(pairs, model, device, batch_size=32)')
+                   api='dust3r_b200.inference.inference(pairs, model, device, batch_size=32)', host_inputs='pinned')
+        # the same call with PAGEABLE host images (what the reference's load_images yields): inference() stages them through
+        # pinned memory itself
+        pairs_pg = synth_pairs_host(B, seed=99 + rank, pin=False)
+        inference(pairs_pg, net, device, batch_size=B, verbose=False)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            out = inference(pairs_pg, net, device, batch_size=B, verbose=False)
+            _ = float(out['pred1']['conf'][0, 0, 0])
+        torch.cuda.synchronize()
+        dtp = torch.tensor([time.perf_counter() - t0], device=device)
+        if world > 1:
+            dist.all_reduce(dtp, op=dist.ReduceOp.MAX)
+        e2e['pageable_inputs'] = dict(value=world * B * n_e2e / float(dtp[0]), unit='image-pairs/s')
 
     if rank != 0:
         if world > 1:
@@ -470,6 +529,11 @@ def main():
         del packed, net, imgs
         torch.cuda.empty_cache()
         line['cloud_opt'] = cloud_opt_section(device, pk)
+        torch.cuda.empty_cache()
+        try:
+            line['cloud_opt_config5'] = cloud_opt_config5_section(device, pk)
+        except torch.cuda.OutOfMemoryError as ex:      # 16 GB of observations: needs a mostly free GPU
+            line['cloud_opt_config5'] = dict(unavailable=f'out of memory: {ex}')
     if world == 1 and not args.skip_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline_forward(1)
         if not args.skip_cloud_opt:

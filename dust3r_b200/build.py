@@ -56,7 +56,19 @@ def _compile(src, log):
     return obj
 
 
+def generate_sources():
+    """csrc/gemm2_tcgen05.cuh (the CTA-pair GEMM kernel) is a mechanical derivation of csrc/gemm_tcgen05.cuh: it is generated
+    here (scripts/gen_gemm2.py) and not kept under version control, so an epilogue exists in exactly one source."""
+    gen = os.path.join(HERE, '..', 'scripts', 'gen_gemm2.py')
+    src, dst = os.path.join(CSRC, 'gemm_tcgen05.cuh'), os.path.join(CSRC, 'gemm2_tcgen05.cuh')
+    if not os.path.exists(dst) or os.path.getmtime(dst) < max(os.path.getmtime(src), os.path.getmtime(gen)):
+        r = subprocess.run([sys.executable, gen], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f'gen_gemm2.py failed:\n{r.stdout}\n{r.stderr}')
+
+
 def build(force=False, verbose=False):
+    generate_sources()
     os.makedirs(OBJ_DIR, exist_ok=True)
     if force:
         for f in os.listdir(OBJ_DIR):

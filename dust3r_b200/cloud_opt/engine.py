@@ -397,7 +397,7 @@ class AlignEngine:
         d = self._desc()
         self._call(self.lib.d3r_align_overflow_flag, C.byref(d), C.byref(flag))
         if flag.value:
-            raise _lib.D3RError('alignment: a gradient partial sum exceeded the fixed-point accumulator range (|x| >= 2^18); '
+            raise _lib.D3RError('alignment: a gradient sum left the fixed-point accumulator range (partial >= 2^18 or total >= 2^22, or NaN / Inf); '
                                 'rescale the scene (pointmaps are expected in metric-like units)')
 
     def evaluate_loss(self):

@@ -55,22 +55,26 @@ inline int64_t workspace_floats(int n, int E) {
          align4(int64_t(2) * E * kEdgeT) + align4(int64_t(E) * 24) + align4(int64_t(n) * 20);
 }
 
-// Order-independent (hence deterministic) cross-CTA accumulation: every CTA contributes its exactly-ordered fp32
-// partial sum as a 2^44 fixed-point integer through a 64-bit integer atomic.  Resolution 5.7e-14, range +-5e5.
-constexpr double kFixScale = 17592186044416.0;        // 2^44
-constexpr double kFixInv = 1.0 / 17592186044416.0;
+// Order-independent (hence deterministic) cross-CTA accumulation: every warp contributes its exactly-ordered fp32
+// partial sum as a 2^40 fixed-point integer through a 64-bit integer atomic.  Resolution 9.1e-13 (the sums are O(1..100) and
+// end up in fp32), range +-8.4e6.  Overflow is reported, not silently wrapped: a partial must stay below 2^18 (checked where it
+// is added; also catches NaN / Inf) and a total below 2^22 (checked where it is read) -- 16 partials at the limit would be needed
+// to wrap the accumulator unnoticed, versus 2 with the 2^44 scale of round 1.
+constexpr double kFixScale = 1099511627776.0;        // 2^40
 __device__ __forceinline__ void fix_add(long long* dst, float x, int* overflow_flag) {
   if (!(fabsf(x) < 262144.f)) *overflow_flag = 1;     // also catches NaN / Inf
   const long long q = __double2ll_rn(double(x) * kFixScale);
   atomicAdd(reinterpret_cast<unsigned long long*>(dst), static_cast<unsigned long long>(q));
 }
-// 2^-44 * q without FP64 (int64 -> double conversions are multi-pass on sm_100 and sit on the small step's critical path):
-// q = hi * 2^32 + lo; hi * 2^-12 carries the value, lo * 2^-44 < 2^-12 the fraction below.
-__device__ __forceinline__ float fix_get(const long long* src) {
+// 2^-40 * q without FP64 (int64 -> double conversions are multi-pass on sm_100 and sit on the small step's critical path):
+// q = hi * 2^32 + lo; hi * 2^-8 carries the value, lo * 2^-40 < 2^-8 the fraction below.
+__device__ __forceinline__ float fix_get(const long long* src, int* overflow_flag) {
   const long long q = __ldcg(src);
   const int hi = int(q >> 32);
   const unsigned lo = unsigned(q);
-  return fmaf(__uint2float_rn(lo), 5.6843418860808015e-14f /* 2^-44 */, __int2float_rn(hi) * 2.44140625e-4f /* 2^-12 */);
+  const float v = fmaf(__uint2float_rn(lo), 9.094947017729282e-13f /* 2^-40 */, __int2float_rn(hi) * 3.90625e-3f /* 2^-8 */);
+  if (!(fabsf(v) < 4194304.f)) *overflow_flag = 1;    // |total| >= 2^22: out of the supported range
+  return v;
 }
 
 // Grid ticket: release this CTA's accumulations / log-depth updates and acquire everybody else's in ONE operation by one
@@ -271,7 +275,7 @@ static __device__ __noinline__ void small_param_step(const d3r_align_desc& D, co
 
   // phase 0: loss (fixed order over entries) and mean log-scale, one barrier
   float lpart = 0.f, spart = 0.f;
-  for (int k = threadIdx.x; k < 2 * E; k += blockDim.x) lpart += fix_get(ws.ent_acc + k * kEntVals + 12);
+  for (int k = threadIdx.x; k < 2 * E; k += blockDim.x) lpart += fix_get(ws.ent_acc + k * kEntVals + 12, ws.flags);
   for (int e = threadIdx.x; e < E; e += blockDim.x) spart += sm[L.pw + e * 8 + 7];
   lpart = warp_sum(lpart);
   spart = warp_sum(spart);
@@ -295,7 +299,7 @@ static __device__ __noinline__ void small_param_step(const d3r_align_desc& D, co
       for (int k = 0; k < 8; ++k) p8[k] = sm[L.pw + e * 8 + k];
       const float a0 = sm[L.adapt + e * 2 + 0], a1 = sm[L.adapt + e * 2 + 1];
 #pragma unroll
-      for (int k = 0; k < 12; ++k) { si[k] = fix_get(ws.ent_acc + ei * kEntVals + k); sj[k] = fix_get(ws.ent_acc + ej * kEntVals + k); }
+      for (int k = 0; k < 12; ++k) { si[k] = fix_get(ws.ent_acc + ei * kEntVals + k, ws.flags); sj[k] = fix_get(ws.ent_acc + ej * kEntVals + k, ws.flags); }
       EdgeGeom g;
       edge_geom(p8, a0, a1, D, mean_sigma, log_base, g);
       float dM[9], dt[3];
@@ -340,7 +344,7 @@ static __device__ __noinline__ void small_param_step(const d3r_align_desc& D, co
       for (int k = 0; k < 7; ++k) q7[k] = sm[L.poses + i * 7 + k];
       const float f0 = sm[L.focals + i * 2 + 0], f1 = sm[L.focals + i * 2 + 1];
 #pragma unroll
-      for (int k = 0; k < 12; ++k) S[k] = fix_get(ws.img_acc + i * kImgVals + k);   // S[a*3+b] = sum G_a c_b ; S[9+a] = sum G_a
+      for (int k = 0; k < 12; ++k) S[k] = fix_get(ws.img_acc + i * kImgVals + k, ws.flags);   // S[a*3+b] = sum G_a c_b ; S[9+a] = sum G_a
       float R[9], qh[4], qn;
       quat_to_R(q7, R, qh, &qn);
       if (D.stream_kernel) {
@@ -469,7 +473,7 @@ static __device__ __forceinline__ void small_param_step_fast(const d3r_align_des
     for (int k = 0; k < kGeomE / 4; ++k) { const float4 t = c4[k]; c[4 * k] = t.x; c[4 * k + 1] = t.y; c[4 * k + 2] = t.z; c[4 * k + 3] = t.w; }
     float si[13], sj[13];
 #pragma unroll
-    for (int k = 0; k < 13; ++k) { si[k] = fix_get(ws.ent_acc + ei * kEntVals + k); sj[k] = fix_get(ws.ent_acc + ej * kEntVals + k); }
+    for (int k = 0; k < 13; ++k) { si[k] = fix_get(ws.ent_acc + ei * kEntVals + k, ws.flags); sj[k] = fix_get(ws.ent_acc + ej * kEntVals + k, ws.flags); }
 #pragma unroll
     for (int k = 0; k < kEntVals; ++k) { ws.ent_acc[ei * kEntVals + k] = 0; ws.ent_acc[ej * kEntVals + k] = 0; }   // read: clear for the next launch
     lpart = si[12] + sj[12];
@@ -514,7 +518,7 @@ static __device__ __forceinline__ void small_param_step_fast(const d3r_align_des
     for (int k = 0; k < kGeomI / 4; ++k) { const float4 t = c4[k]; c[4 * k] = t.x; c[4 * k + 1] = t.y; c[4 * k + 2] = t.z; c[4 * k + 3] = t.w; }
     float S[12];
 #pragma unroll
-    for (int k = 0; k < 12; ++k) S[k] = fix_get(ws.img_acc + i * kImgVals + k);   // S[a*3+b] = sum G_a c_b ; S[9+a] = sum G_a
+    for (int k = 0; k < 12; ++k) S[k] = fix_get(ws.img_acc + i * kImgVals + k, ws.flags);   // S[a*3+b] = sum G_a c_b ; S[9+a] = sum G_a
 #pragma unroll
     for (int k = 0; k < kImgVals; ++k) ws.img_acc[i * kImgVals + k] = 0;
     const float* R = c;

@@ -2,7 +2,7 @@
 //
 //   O = softmax(Q K^T * scale) V      per (image b, head h), bf16 in/out, fp32 softmax + accumulation
 //
-// Same dataflow as attention_tc.cu (TMA producer warp, single-thread MMA issuer, S and O in TMEM, P through
+// (TMA producer warp, single-thread MMA issuer, S and O in TMEM, P through
 // 128B-swizzled shared memory) with the softmax work of one 128-query tile spread over EIGHT warps instead of four:
 // the two warps that own a TMEM lane quarter (32 query rows) each take half of the 128 keys of a block, so the
 // per-block serial chain of a thread (TMEM load -> 64 exp2 -> P store -> fence -> barrier) is half as long for the

@@ -1,4 +1,4 @@
-// Helpers shared by the tcgen05 attention kernels (attention_tc.cu, attention_tc2.cu).
+// Helpers shared by the tcgen05 attention kernels (attention_tc2.cu, attention_tc3.cu).
 #pragma once
 #include "d3r_common.cuh"
 #include "sm100_ptx.cuh"

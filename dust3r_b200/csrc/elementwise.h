@@ -1,4 +1,4 @@
-// Internal host API of the bandwidth-bound glue kernels (elementwise.cu) and attention (attention.cu).
+// Internal host API of the bandwidth-bound glue kernels (elementwise.cu) and attention (attention_dispatch.cu).
 #pragma once
 #include <cuda_runtime.h>
 #include <cstddef>
@@ -19,7 +19,7 @@ namespace attn {
 // q rows: (b*Nq + i)*ldq + h*64 ; k/v rows: (b*Nk + j)*ldk(v) + h*64.
 int attention_hd64(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
                    long long ldo, int B, int heads, int Nq, int Nk, float scale, cudaStream_t st);
-int attention_hd64_tc(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
+int attention_hd64_tc3(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
                       long long ldo, int B, int heads, int Nq, int Nk, float scale, cudaStream_t st);
 int attention_hd64_tc2(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
                       long long ldo, int B, int heads, int Nq, int Nk, float scale, cudaStream_t st);

@@ -177,12 +177,25 @@ class AsymmetricCroCo3DStereo(nn.Module, _HubMixin, **_hub_kwargs):
                     p.requires_grad = False
 
     # ---------------------------------------------------------------- weight repacking
+    def _param_version(self):
+        """Sum of the parameters' in-place modification counters: changes whenever a weight is edited in place
+        (p.data.copy_, optimizer steps, ...), which load_state_dict / .to() hooks cannot see."""
+        return sum(p._version for p in self.parameters())
+
     def repack(self):
-        """(Re)build the kernel-side operand buffers from the current parameters."""
+        """(Re)build the kernel-side operand buffers (bf16 GEMM operands, fp32 biases / LayerNorm parameters) from the
+        current parameters.  forward() calls it by itself when the parameters changed since the last packing."""
         dev = next(self.parameters()).device
         _lib.require_cuda_device(dev)
         self._packed = _PackedModel(self, dev)
+        self._packed_version = self._param_version()
         return self._packed
+
+    def _ensure_packed(self, dev):
+        if self._packed is None or self._packed.device != dev or getattr(self, '_packed_version', None) != self._param_version():
+            if next(self.parameters()).device != dev:
+                raise _lib.D3RError(f'model parameters live on {next(self.parameters()).device}, images on {dev}')
+            self.repack()
 
     # ---------------------------------------------------------------- forward
     @torch.no_grad()
@@ -191,10 +204,7 @@ class AsymmetricCroCo3DStereo(nn.Module, _HubMixin, **_hub_kwargs):
         B = img1.shape[0]
         dev = img1.device
         _lib.require_cuda_device(dev)
-        if self._packed is None or self._packed.device != dev:
-            if next(self.parameters()).device != dev:
-                raise _lib.D3RError(f'model parameters live on {next(self.parameters()).device}, images on {dev}')
-            self.repack()
+        self._ensure_packed(dev)
         H, W = int(img1.shape[-2]), int(img1.shape[-1])
         H2, W2 = int(img2.shape[-2]), int(img2.shape[-1])
         shape1 = torch.as_tensor(view1.get('true_shape', torch.tensor(img1.shape[-2:])[None].repeat(B, 1))).cpu()
@@ -274,10 +284,7 @@ class AsymmetricCroCo3DStereo(nn.Module, _HubMixin, **_hub_kwargs):
         run per pair.  Same outputs as forward() on the expanded batch."""
         dev = imgs.device
         _lib.require_cuda_device(dev)
-        if self._packed is None or self._packed.device != dev:
-            if next(self.parameters()).device != dev:
-                raise _lib.D3RError(f'model parameters live on {next(self.parameters()).device}, images on {dev}')
-            self.repack()
+        self._ensure_packed(dev)
         B = len(idx1)
         assert len(idx2) == B and B > 0
         H, W = int(imgs.shape[-2]), int(imgs.shape[-1])

@@ -166,8 +166,9 @@ int64_t d3r_align_workspace_floats(int32_t n_imgs, int32_t n_edges, int32_t n_ch
 int d3r_align_prepare(const d3r_align_desc* desc, void* stream);
 /* Runs iterations [it_begin, it_end) (indices into sched / loss_out).  Asynchronous. */
 int d3r_align_run(const d3r_align_desc* desc, int32_t it_begin, int32_t it_end, void* stream);
-/* Cross-CTA sums use order-independent 2^44 fixed-point integer atomics (bit-reproducible).  *host_out = 1 when a
- * partial sum left their range (|x| >= 2^18: unreasonably scaled scene) since the workspace was zeroed. */
+/* Cross-CTA sums use order-independent 2^40 fixed-point integer atomics (bit-reproducible).  *host_out = 1 when a
+ * partial sum (|x| >= 2^18) or a total (|x| >= 2^22) left the supported range (unreasonably scaled scene, NaN / Inf input)
+ * since iteration 0 of the current d3r_align_run batch. */
 int d3r_align_overflow_flag(const d3r_align_desc* desc, int32_t* host_out, void* stream);
 /* World-frame pointmaps X[i] = R_i * unproject(depth_i) + T_i for every image
  * (PointCloudOptimizer.depth_to_pts3d, optimizer.py:170-180).  out: [sum P_i][3] float. */
@@ -252,9 +253,8 @@ void d3r_set_gemm_pair_min_kblocks(int32_t kblocks);
 /* Debug aid: per-image timeline stamps (64 x uint64 %globaltimer per traced CTA) of the tcgen05 attention. */
 int d3r_attention_set_debug(void* dev_buf);
 
-/* Selects the attention kernel: 0 = mma.sync streaming kernel, 1 = tcgen05/TMEM kernel (one thread per query row,
- * 64-key blocks, 3 CTAs/SM), 2 = tcgen05/TMEM split-row kernel (two warps per 32 rows, 128-key blocks, P through shared
- * memory), 3 (default) = the same with P kept in tensor memory (A-from-TMEM tcgen05.mma). */
+/* Selects the attention kernel: 3 (default) = tcgen05/TMEM split-row kernel (two warps per 32 query rows, 128-key blocks) with P
+ * kept in tensor memory (A-from-TMEM tcgen05.mma); 2 = the same dataflow with P through shared memory (A/B reference). */
 void d3r_set_attention_impl(int32_t impl);
 
 /* ------------------------------------------------------------------------------------------

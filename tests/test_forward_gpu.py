@@ -40,7 +40,7 @@ def _rel(a, b):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize('impl', [0, 1, 2, 3])
+@pytest.mark.parametrize('impl', [2, 3])
 def test_attention_matches_torch(cuda_device, impl):
     from dust3r_b200 import _lib
     lib = _lib.get_lib()
@@ -322,3 +322,20 @@ def test_landscape_only_many_ar_batch_matches_reference_golden(cuda_device, name
         assert got.shape == ref.shape
         for k in range(4):
             assert _rel(got[k].cpu(), ref[k]) < 3e-2, (name, key, k, _rel(got[k].cpu(), ref[k]))
+
+
+def test_in_place_weight_edit_is_picked_up(cuda_device):
+    """The kernel-side operand buffers are rebuilt when a parameter was modified in place since the last packing."""
+    cfg, H, W = _small_cfgs()['small_linear']
+    net, sd = _build(cfg, 11, cuda_device)
+    imgs = synth_images(2, H, W, seed=8)
+    v1 = dict(img=imgs[0]['img'].to(cuda_device), instance=['0'])
+    v2 = dict(img=imgs[1]['img'].to(cuda_device), instance=['1'])
+    a, _ = net(v1, v2)
+    a = a['pts3d'].clone()
+    b, _ = net(v1, v2)
+    assert torch.equal(a, b['pts3d'])
+    with torch.no_grad():
+        net.enc_norm.weight.mul_(1.5)
+    c, _ = net(v1, v2)
+    assert not torch.equal(a, c['pts3d'])
