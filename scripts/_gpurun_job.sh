@@ -1,10 +1,4 @@
 mkdir -p gpurun_out
-(time timeout 1200 python -m pytest tests -m gpu -x -q) 2>&1 | tail -6
-(time timeout 900 python bench.py) > gpurun_out/r02_bench_v3.json 2> gpurun_out/bench.err; python - <<'PY'
-import json
-d=json.load(open('gpurun_out/r02_bench_v3.json'))
-print(d['value'], d['ms_per_step'], d['e2e'], d['roofline']['whole_step']['frac'], d.get('cpu_baseline'))
-for k in ('cloud_opt','cloud_opt_config5'):
-    c=d.get(k); print(k, {kk: c[kk] for kk in c if kk not in ('config','roofline')} , c.get('roofline',{}).get('frac'))
-PY
-tail -5 gpurun_out/bench.err
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:align_stream -s 3 -c 1 -o gpurun_out/r02_prof_align_stream_v4 python scripts/ncu_target.py align > gpurun_out/ncu_align.log 2>&1; tail -2 gpurun_out/ncu_align.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention_tc3 -s 2 -c 1 -o gpurun_out/r02_prof_attn_tc3_v3 python scripts/ncu_attn_target.py 3 > gpurun_out/ncu_attn.log 2>&1; tail -2 gpurun_out/ncu_attn.log
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file gpurun_out/r02_ncu_launches_v1.csv python scripts/ncu_target.py forward 32 > gpurun_out/ncu_fwd.log 2>&1; tail -2 gpurun_out/ncu_fwd.log; wc -l gpurun_out/r02_ncu_launches_v1.csv
