@@ -339,3 +339,30 @@ def test_in_place_weight_edit_is_picked_up(cuda_device):
         net.enc_norm.weight.mul_(1.5)
     c, _ = net(v1, v2)
     assert not torch.equal(a, c['pts3d'])
+
+
+@pytest.mark.timeout(1200)
+@pytest.mark.parametrize('name', ['small_linear', 'small_dpt'])
+@pytest.mark.parametrize('depth_mode,conf_mode', [('linear', ('exp', 1, float('inf'))), ('square', ('sigmoid', 0.5, 4.0)),
+                                                   ('exp', None), ('linear', ('sigmoid', 0, 1))])
+def test_postprocess_modes_match_oracle(cuda_device, name, depth_mode, conf_mode):
+    """heads/postprocess.py:10-58: every depth mode (linear / square / exp) and confidence mode (exp / sigmoid / none) through
+    both head tails (the fused DPT epilogue and the linear head's pixel-shuffle kernel)."""
+    import copy
+    from oracle.forward_oracle import forward_oracle
+    cfg0, H, W = _small_cfgs()[name]
+    cfg = copy.deepcopy(cfg0)
+    cfg.depth_mode = (depth_mode, -float('inf'), float('inf'))
+    cfg.conf_mode = conf_mode
+    net, sd = _build(cfg, 11, cuda_device)
+    imgs = synth_images(2, H, W, seed=5)
+    v1 = dict(img=imgs[0]['img'].to(cuda_device), instance=['0'])
+    v2 = dict(img=imgs[1]['img'].to(cuda_device), instance=['1'])
+    r1, r2 = net(v1, v2)
+    o1, o2 = forward_oracle(sd, cfg, imgs[0]['img'], imgs[1]['img'])
+    assert ('conf' in r1) == (conf_mode is not None) == ('conf' in o1)
+    assert _rel(r1['pts3d'].cpu(), o1['pts3d']) < 3e-2 and _rel(r2['pts3d_in_other_view'].cpu(), o2['pts3d_in_other_view']) < 3e-2
+    if conf_mode is not None:
+        assert _rel(r1['conf'].cpu(), o1['conf']) < 3e-2 and _rel(r2['conf'].cpu(), o2['conf']) < 3e-2
+        lo, hi = conf_mode[1], conf_mode[2]
+        assert float(r1['conf'].min()) >= lo - 1e-6 and float(r1['conf'].max()) <= hi + 1e-6
