@@ -11,7 +11,9 @@
 //     and the PV MMA reads 16 KB of shared memory (V) instead of 48 KB.  TMEM: S [0,128) | P [128,192) | O [192,256).
 //   * the per-key instruction count is cut from ~4.5 to 3: the exponent argument of a key PAIR comes from one packed FFMA2,
 //     the row sum from one packed FADD2, the running maximum from one packed HMNMX2 on the bf16 pair that goes to TMEM;
-//     TMEM reads of S are software-pipelined against the exponentials, 16 keys at a time.  (ex2.approx.ftz.bf16x2 was
+//     TMEM reads of S are software-pipelined against the exponentials, 16 keys at a time; every 4th key pair takes its two
+//     exponentials on the FMA pipe (Cody-Waite + degree-3 polynomial, rel. error 7.5e-5), because the MUFU is the busiest unit
+//     of the kernel (54 % active against 42 % of the issue slots).  (ex2.approx.ftz.bf16x2 was
 //     measured: same MUFU time per key as fp32 -- 16.5 / clk / SM either way -- and 2-3 % error on the dominant keys once
 //     the lazy reference lets the exponent grow to +8; the exponentials stay fp32.)
 // Softmax bookkeeping lives in the log2 domain: t = s * scale * log2(e), reference `ms`, x = t - ms, p = 2^x.  The per-row
@@ -48,6 +50,7 @@ typedef unsigned long long f2;               // two packed fp32
 __device__ __forceinline__ f2 pk2(float lo, float hi) { f2 d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi)); return d; }
 __device__ __forceinline__ void upk2(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ f2 fadd2(f2 a, f2 b) { f2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 fsub2(f2 a, f2 b) { f2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f2 ffma2(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 // {hi, lo} fp32 -> packed bf16x2 (lo in the low half: the even key of a pair)
 __device__ __forceinline__ uint32_t cvt_bf16x2(float hi, float lo) {
@@ -79,7 +82,25 @@ __device__ __forceinline__ void pair_barrier(int quarter) {
 __device__ unsigned long long* g_attn3_dbg = nullptr;
 #define A3_STAMP(gg, slot) do { if (dbg && (gg) >= 10u && (gg) < 14u) dbg[((gg) - 10u) * 16 + (slot)] = (unsigned long long)clock64(); } while (0)
 
-template <int ABL>   // ABL: timing ablation (debug; results are wrong for ABL != 0): 1 = no exponentials
+// 2^x for a key pair on the FMA pipe (Cody-Waite split + degree-3 minimax on [-0.5, 0.5], rel. error 7.5e-5 -- far below the bf16
+// rounding of P): offloads a share of the exponentials from the MUFU, the busiest unit of this kernel (54 % vs 42 % issue slots)
+__device__ __forceinline__ f2 poly_exp2_pair(f2 x) {
+  float x0, x1;
+  upk2(x, x0, x1);
+  x = pk2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const f2 magic = pk2(12582912.f, 12582912.f);           // 1.5 * 2^23: the low mantissa bits of t hold round(x)
+  const f2 t = fadd2(x, magic);
+  const f2 r = fadd2(x, fsub2(magic, t));                   // x - (t - magic) in [-0.5, 0.5]
+  f2 p = ffma2(pk2(0.0551716648f, 0.0551716648f), r, pk2(0.2426111549f, 0.2426111549f));
+  p = ffma2(p, r, pk2(0.6932609677f, 0.6932609677f));
+  p = ffma2(p, r, pk2(0.9999280572f, 0.9999280572f));
+  float p0, p1, t0, t1;
+  upk2(p, p0, p1);
+  upk2(t, t0, t1);
+  return pk2(__int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23)), __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23)));
+}
+
+template <int ABL, int POLY>   // ABL: timing ablation (debug; results are wrong for ABL != 0): 1 = no exponentials; POLY: every POLY-th pair on the FMA pipe (0 = none)
 __global__ void __launch_bounds__(kThreads, 2)
 attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, __nv_bfloat16* __restrict__ out, long long ldo, int Nq, int Nk,
@@ -270,7 +291,13 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
               if (c0 + 2 * i >= nvalid) x0 = -INFINITY;
               if (c0 + 2 * i + 1 >= nvalid) x1 = -INFINITY;
             }
-            const float p0 = (ABL >= 1) ? x0 : fast_exp2(x0), p1 = (ABL >= 1) ? x1 : fast_exp2(x1);
+            float p0, p1;
+            if (POLY > 0 && !decltype(masked)::value && (i % (POLY > 0 ? POLY : 1)) == (POLY > 0 ? POLY : 1) - 1) {
+              upk2(poly_exp2_pair(x), p0, p1);
+            } else {
+              p0 = (ABL >= 1) ? x0 : fast_exp2(x0);
+              p1 = (ABL >= 1) ? x1 : fast_exp2(x1);
+            }
             lsum2 = fadd2(lsum2, pk2(p0, p1));
             const uint32_t pb = cvt_bf16x2(p1, p0);
             pmax = max_bf16x2(pmax, pb);
@@ -409,23 +436,24 @@ int attention_tc3_set_debug(void* dev_buf) {
   return D3R_OK;
 }
 
+constexpr int kDefaultPoly = 4;   // measured (64,16,768,768): none 0.272 ms, every 4th pair 0.243, every 3rd 0.245, every 2nd 0.261
 static int g_tc3_ablation = 0;
 void set_tc3_ablation(int a) { g_tc3_ablation = a; }
 
-template <int ABL>
+template <int ABL, int POLY>
 static int launch_tc3(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, void* out, long long ldo, int B, int heads,
                       int Nq, int Nk, float scale, cudaStream_t st) {
   // per device: a process may drive several GPUs and the opt-in is a per-context function attribute
-  D3R_CUDA(cudaFuncSetAttribute(tc3::attention_tc3_kernel<ABL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::kSmemBytes));
+  D3R_CUDA(cudaFuncSetAttribute(tc3::attention_tc3_kernel<ABL, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::kSmemBytes));
   // two CTAs per SM only fit with the maximum shared-memory carve-out
-  D3R_CUDA(cudaFuncSetAttribute(tc3::attention_tc3_kernel<ABL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  D3R_CUDA(cudaFuncSetAttribute(tc3::attention_tc3_kernel<ABL, POLY>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   const int total_tiles = ((Nq + tc3::BQ - 1) / tc3::BQ) * heads * B;
   const int slots = 2 * num_sms();   // two persistent CTAs per SM
   // equal number of tiles per CTA where possible: a grid of `slots` CTAs would leave a ragged last round
   const int rounds = (total_tiles + slots - 1) / slots;
   const int grid = (total_tiles + rounds - 1) / rounds;
   prof::Scope scope("attention_tcgen05_tmemP", st, 4.0 * double(B) * heads * double(Nq) * double(Nk) * 64.0);
-  D3R_CUDA(pdl::launch(tc3::attention_tc3_kernel<ABL>, dim3(grid), dim3(tc3::kThreads), size_t(tc3::kSmemBytes), st, mq, mk, mv,
+  D3R_CUDA(pdl::launch(tc3::attention_tc3_kernel<ABL, POLY>, dim3(grid), dim3(tc3::kThreads), size_t(tc3::kSmemBytes), st, mq, mk, mv,
                        (__nv_bfloat16*)out, ldo, Nq, Nk, heads, total_tiles, scale * 1.4426950408889634f));
   D3R_LAUNCH_CHECK();
   return D3R_OK;
@@ -442,8 +470,13 @@ int attention_hd64_tc3(const void* q, long long ldq, const void* k, long long ld
   if ((rc = tcc::make_map(&mq, q, ldq, heads * 64, Nq, B, tc3::BQ))) return rc;
   if ((rc = tcc::make_map(&mk, k, ldk, heads * 64, Nk, B, tc3::BK))) return rc;
   if ((rc = tcc::make_map(&mv, v, ldv, heads * 64, Nk, B, tc3::BK))) return rc;
-  if (g_tc3_ablation == 1) return launch_tc3<1>(mq, mk, mv, out, ldo, B, heads, Nq, Nk, scale, st);
-  return launch_tc3<0>(mq, mk, mv, out, ldo, B, heads, Nq, Nk, scale, st);
+  switch (g_tc3_ablation) {   // debug encodings (d3r_set_attention_impl(3 + 10 k)): 1 = no exponentials; 2 / 3 / 4 = every 4th / 3rd / 2nd pair on the FMA pipe
+    case 1: return launch_tc3<1, 0>(mq, mk, mv, out, ldo, B, heads, Nq, Nk, scale, st);
+    case 2: return launch_tc3<0, 4>(mq, mk, mv, out, ldo, B, heads, Nq, Nk, scale, st);
+    case 3: return launch_tc3<0, 3>(mq, mk, mv, out, ldo, B, heads, Nq, Nk, scale, st);
+    case 4: return launch_tc3<0, 2>(mq, mk, mv, out, ldo, B, heads, Nq, Nk, scale, st);
+    default: return launch_tc3<0, kDefaultPoly>(mq, mk, mv, out, ldo, B, heads, Nq, Nk, scale, st);
+  }
 }
 
 }  // namespace attn

@@ -1,3 +1,8 @@
-timeout 900 python -m pytest tests/test_forward_gpu.py -x -q -k "postprocess_modes" 2>&1 | tail -6
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_align_gpu.py -x -q -k "first_iterations or ragged_image or entry_window or fx_and_fy" 2>&1 | tail -6
-timeout 600 compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_forward_gpu.py tests/test_scene_ops_gpu.py -x -q -k "attention or kernel_matches" 2>&1 | tail -6
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_forward_gpu.py -x -q 2>&1 | tail -4
+timeout 900 python bench.py --skip-cpu-baseline --skip-cloud-opt > gpurun_out/r02_bench_v4.json 2> gpurun_out/bench.err; python - <<'PY'
+import json
+d=json.load(open('gpurun_out/r02_bench_v4.json'))
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['whole_step']['frac'])
+for k,v in list(d['kernels'].items())[:8]: print(k, v['ms'], v['tflops'], v['gbs'])
+PY
