@@ -152,42 +152,72 @@ int patch_im2col16(const float* img, void* out, int B, int H, int W, cudaStream_
 }
 
 // ---- bilinear x2 upsample, align_corners=True, NHWC bf16 (F.interpolate in dpt_block.py:226,247) ----
+// One thread = one 16-byte channel vector of one output column, walking kRowsPerBlock consecutive output rows.  An input row
+// feeds two to three output rows: the thread keeps the two source rows of the current output row (2 x 2 vectors) in registers
+// and fetches a new pair only when the source row advances, so a vector of output costs ~1.3 instead of 4 loads -- the
+// one-output-per-thread version was bound by L2 -> L1 traffic (64 B read per 16 B written, 2.3 TB/s of output).
+constexpr int kUpRows = 8;
+__device__ __forceinline__ uint4 lerp4(const uint4& a, const uint4& b, const uint4& c, const uint4& d, float w00, float w01, float w10,
+                                       float w11) {
+  const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w}, cv[4] = {c.x, c.y, c.z, c.w}, dv[4] = {d.x, d.y, d.z, d.w};
+  uint32_t r[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const __nv_bfloat162 ha = *reinterpret_cast<const __nv_bfloat162*>(&av[t]);
+    const __nv_bfloat162 hb = *reinterpret_cast<const __nv_bfloat162*>(&bv[t]);
+    const __nv_bfloat162 hc = *reinterpret_cast<const __nv_bfloat162*>(&cv[t]);
+    const __nv_bfloat162 hd = *reinterpret_cast<const __nv_bfloat162*>(&dv[t]);
+    const float lo = w00 * __low2float(ha) + w01 * __low2float(hb) + w10 * __low2float(hc) + w11 * __low2float(hd);
+    const float hi = w00 * __high2float(ha) + w01 * __high2float(hb) + w10 * __high2float(hc) + w11 * __high2float(hd);
+    r[t] = pack2(lo, hi);
+  }
+  return make_uint4(r[0], r[1], r[2], r[3]);
+}
 __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                           int H, int W, int C, int Ho, int Wo, int vpc_shift) {
   pdl::sync_with_predecessor();   // PDL: nothing above touches memory produced by other kernels
-  // grid = (x tiles, Ho, B): the row interpolation terms are block-uniform, no per-thread div/mod chain
-  const int oy = blockIdx.y, b = blockIdx.z;
+  // grid = (x tiles, row groups, B)
+  const int b = blockIdx.z;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int vpc = 1 << vpc_shift;
   const int ox = idx >> vpc_shift, v = idx & (vpc - 1);
   if (ox >= Wo) return;
   // source coordinate for an output grid of (2H, 2W) (cropping keeps the scale of the full map)
-  const float sy = (H > 1) ? oy * (float(H - 1) / float(2 * H - 1)) : 0.f;
   const float sx = (W > 1) ? ox * (float(W - 1) / float(2 * W - 1)) : 0.f;
-  const int y0 = (int)sy, x0 = (int)sx;
-  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
-  const float fy = sy - y0, fx = sx - x0;
-  const __nv_bfloat16* r0 = x + ((size_t)b * H + y0) * W * C + v * 8;
-  const __nv_bfloat16* r1 = x + ((size_t)b * H + y1) * W * C + v * 8;
-  const uint4 p00 = __ldg(reinterpret_cast<const uint4*>(r0 + (size_t)x0 * C));
-  const uint4 p01 = __ldg(reinterpret_cast<const uint4*>(r0 + (size_t)x1 * C));
-  const uint4 p10 = __ldg(reinterpret_cast<const uint4*>(r1 + (size_t)x0 * C));
-  const uint4 p11 = __ldg(reinterpret_cast<const uint4*>(r1 + (size_t)x1 * C));
-  const uint32_t a[4] = {p00.x, p00.y, p00.z, p00.w}, bq[4] = {p01.x, p01.y, p01.z, p01.w};
-  const uint32_t c[4] = {p10.x, p10.y, p10.z, p10.w}, d[4] = {p11.x, p11.y, p11.z, p11.w};
-  uint32_t r[4];
-  const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const __nv_bfloat162 ha = *reinterpret_cast<const __nv_bfloat162*>(&a[t]);
-    const __nv_bfloat162 hb = *reinterpret_cast<const __nv_bfloat162*>(&bq[t]);
-    const __nv_bfloat162 hc = *reinterpret_cast<const __nv_bfloat162*>(&c[t]);
-    const __nv_bfloat162 hd = *reinterpret_cast<const __nv_bfloat162*>(&d[t]);
-    const float lo = w00 * __low2float(ha) + w01 * __low2float(hb) + w10 * __low2float(hc) + w11 * __low2float(hd);
-    const float hi = w00 * __high2float(ha) + w01 * __high2float(hb) + w10 * __high2float(hc) + w11 * __high2float(hd);
-    r[t] = pack2(lo, hi);
+  const int x0 = (int)sx;
+  const int x1 = min(x0 + 1, W - 1);
+  const float fx = sx - x0;
+  const __nv_bfloat16* base = x + (size_t)b * H * W * C + v * 8;
+  const int oy_begin = blockIdx.y * kUpRows, oy_end = min(oy_begin + kUpRows, Ho);
+  const float ystep = (H > 1) ? (float(H - 1) / float(2 * H - 1)) : 0.f;
+  int cy0 = -1, cy1 = -1;
+  uint4 a0, a1, c0, c1;            // rows cy0 / cy1 at columns x0 / x1
+  for (int oy = oy_begin; oy < oy_end; ++oy) {
+    const float sy = oy * ystep;
+    const int y0 = (int)sy;
+    const int y1 = min(y0 + 1, H - 1);
+    const float fy = sy - y0;
+    if (y0 != cy0) {
+      if (y0 == cy1) { a0 = c0; a1 = c1; }          // the old lower row becomes the upper one
+      else {
+        const __nv_bfloat16* r0 = base + (size_t)y0 * W * C;
+        a0 = __ldg(reinterpret_cast<const uint4*>(r0 + (size_t)x0 * C));
+        a1 = __ldg(reinterpret_cast<const uint4*>(r0 + (size_t)x1 * C));
+      }
+      cy0 = y0;
+    }
+    if (y1 != cy1) {
+      if (y1 == y0) { c0 = a0; c1 = a1; }           // clamped at the last row
+      else {
+        const __nv_bfloat16* r1 = base + (size_t)y1 * W * C;
+        c0 = __ldg(reinterpret_cast<const uint4*>(r1 + (size_t)x0 * C));
+        c1 = __ldg(reinterpret_cast<const uint4*>(r1 + (size_t)x1 * C));
+      }
+      cy1 = y1;
+    }
+    const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
+    __stcs(reinterpret_cast<uint4*>(out + (((size_t)b * Ho + oy) * Wo + ox) * C + v * 8), lerp4(a0, a1, c0, c1, w00, w01, w10, w11));
   }
-  __stcs(reinterpret_cast<uint4*>(out + (((size_t)b * Ho + oy) * Wo + ox) * C + v * 8), make_uint4(r[0], r[1], r[2], r[3]));
 }
 int upsample2x_bf16(const void* x, void* out, int B, int H, int W, int C, int Ho, int Wo, cudaStream_t st) {
   D3R_CHECK_ARG(C % 8 == 0 && Ho <= 2 * H && Wo <= 2 * W, "upsample2x: bad shape");
@@ -197,7 +227,7 @@ int upsample2x_bf16(const void* x, void* out, int B, int H, int W, int C, int Ho
   while ((1 << shift) < vpc) ++shift;
   const size_t total = (size_t)B * Ho * Wo * vpc;
   prof::Scope scope("upsample2x", st, 0.0, double(total) * 20.0);
-  dim3 grid((unsigned)(((size_t)Wo * vpc + 255) / 256), (unsigned)Ho, (unsigned)B);
+  dim3 grid((unsigned)(((size_t)Wo * vpc + 255) / 256), (unsigned)((Ho + kUpRows - 1) / kUpRows), (unsigned)B);
   D3R_CUDA(pdl::launch(upsample2x_kernel, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)out, H, W, C, Ho, Wo, shift));
   D3R_LAUNCH_CHECK();
   return D3R_OK;
