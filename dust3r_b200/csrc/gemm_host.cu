@@ -72,11 +72,12 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   return D3R_OK;
 }
 
-// 0: 1-CTA kernels, 1: CTA-pair (cta_group::2) kernels whenever BLOCK_N >= 128, 2 (default): pair kernels when
-// the mainloop is long enough to dominate the tile (>= g_pair_min_kb k-blocks), 1-CTA kernels for the short-K
-// decoder projections (measured: profiles/r01_gemm_impl_compare*.jsonl)
+// 0: 1-CTA kernels, 1: CTA-pair (cta_group::2) kernels whenever BLOCK_N >= 128, 2 (default): pair kernels from
+// g_pair_min_kb k-blocks of 64 on, 1-CTA kernels for the shortest reductions (K = 96 / 192 of the DPT re-assembly).
+// Round 1 drew the line at 16 k-blocks from isolated-GEMM timings; interleaved A/B runs of the WHOLE forward step
+// (scripts/gemm_policy_ab.py, round 2) put >= 4 ahead by 1 %: 67.5-67.7 ms against 68.3 ms at >= 16.
 static int g_impl = 2;
-static int g_pair_min_kb = 16;
+static int g_pair_min_kb = 4;
 void set_impl(int impl) { g_impl = impl; }
 void set_pair_min_kb(int kb) { g_pair_min_kb = kb; }
 bool use_pair(int bn, int num_kb) { return bn >= 128 && (g_impl == 1 || (g_impl == 2 && num_kb >= g_pair_min_kb)); }

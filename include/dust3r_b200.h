@@ -245,9 +245,9 @@ int d3r_attention_hd64(const void* q_dev, int64_t ldq, const void* k_dev, int64_
                        void* stream);
 
 /* Selects the GEMM / conv kernel family: 0 = 1-CTA tcgen05 kernels, 1 = CTA-pair (cta_group::2) kernels,
- * 2 (default) = CTA-pair kernels for long-K problems (>= 16 k-blocks of 64), 1-CTA otherwise. */
+ * 2 (default) = CTA-pair kernels from 4 k-blocks of 64 on (K >= 256), 1-CTA for shorter reductions. */
 void d3r_set_gemm_impl(int32_t impl);
-/* Tuning aid for impl 2: minimum number of 64-wide k-blocks for which the CTA-pair kernel is used (default 16). */
+/* Tuning aid for impl 2: minimum number of 64-wide k-blocks for which the CTA-pair kernel is used (default 4). */
 void d3r_set_gemm_pair_min_kblocks(int32_t kblocks);
 
 /* Debug aid: per-image timeline stamps (64 x uint64 %globaltimer per traced CTA) of the tcgen05 attention. */
