@@ -16,13 +16,13 @@ if what in ('forward', 'both'):
     torch.cuda.synchronize()
     del packed, net, imgs
     torch.cuda.empty_cache()
-if what in ('align', 'both'):
-    from dust3r_b200.utils.synth import synth_pair_predictions
-    from dust3r_b200.cloud_opt import global_aligner
-    n = 8
+if what in ('align', 'both', 'align50'):
+    from dust3r_b200.cloud_opt import global_aligner, GlobalAlignerMode
+    from scripts.align_config5 import synth_on_device
+    n = 50 if what == 'align50' else 8      # align50: BASELINE configs[4] (1225 pairs, ModularPointCloudOptimizer)
     edges = [(i, j) for i in range(n) for j in range(i)]
-    out = synth_pair_predictions(n, edges, 384, 512, seed=0)
-    net = global_aligner(out, 'cuda', verbose=False)
+    out = synth_on_device(n, edges, 384, 512, torch.device('cuda'))
+    net = global_aligner(out, 'cuda', mode=GlobalAlignerMode.ModularPointCloudOptimizer if n == 50 else GlobalAlignerMode.PointCloudOptimizer, verbose=False)
     eng = net._get_engine(); net._engine_push(eng)
     eng.run(6)
     torch.cuda.synchronize()
