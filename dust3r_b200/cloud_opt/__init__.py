@@ -24,4 +24,6 @@ def global_aligner(dust3r_output, device, mode=GlobalAlignerMode.PointCloudOptim
         raise NotImplementedError(f'Unknown mode {mode}')
     scene = mode.optimizer_class(dust3r_output['view1'], dust3r_output['view2'], dust3r_output['pred1'], dust3r_output['pred2'],
                                  **optim_kw)
-    return scene.to(device)
+    # non_blocking: predictions that sit in pinned host memory (what inference() returns) are uploaded asynchronously on the
+    # current stream, under the rest of the host-side set-up; pageable sources copy synchronously as before
+    return scene.to(device, non_blocking=True)

@@ -7,6 +7,8 @@ from dust3r_b200.cloud_opt import global_aligner
 n, H, W = 8, 384, 512
 edges = [(i, j) for i in range(n) for j in range(i)]
 out = synth_pair_predictions(n, edges, H, W, seed=0)
+for side in ('pred1', 'pred2'):
+    out[side] = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in out[side].items()}
 def run():
     torch.manual_seed(0)
     net = global_aligner(out, 'cuda', verbose=False)
