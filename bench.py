@@ -228,12 +228,14 @@ def cloud_opt_config5_section(device, pk, n=50, niter=300):
     ms = e0.elapsed_time(e1)
     by = eng.algorithmic_bytes_per_iter()
     gbs = by / (ms / niter) / 1e6
+    tr5 = ncu_traffic().get('align_stream_config5')
     res = dict(metric='cloud_opt iters/sec', value=niter / ms * 1e3, unit='iters/s', ms_per_iter=ms / niter, kernel=eng.kernel,
                config=dict(workload=f'{n} synthetic views -> {E} pairs (symmetrize=False) at 512x384, ModularPointCloudOptimizer, '
                                     f'{niter} iters, lr 0.01 cosine, dist l1, conf log, init=None; predictions resident in HBM'),
                aligner_build_s=round(t_build, 3), loss_first=float(losses[0]), loss_last=float(losses[-1]),
                mem_GB=round(torch.cuda.max_memory_allocated() / 1e9, 1),
-               roofline=dict(bound='hbm', achieved=gbs, peak=pk['hbm'], unit='GB/s', frac=gbs / pk['hbm'], traffic=None,
+               roofline=dict(bound='hbm', achieved=gbs, peak=pk['hbm'], unit='GB/s', frac=gbs / pk['hbm'],
+                             traffic=tr5['bytes'] if tr5 else None, traffic_source=f"{tr5['capture']} @ {tr5['commit']}" if tr5 else None,
                              algorithmic_bytes_per_iter=by, peak_source=pk['source']))
     del net, eng, out
     torch.cuda.empty_cache()
