@@ -357,7 +357,6 @@ class AlignEngine:
         d.loss_out = self.loss_out.data_ptr()
         d.counters = self.counters.data_ptr()
         d.stream_kernel = 1 if self.kernel == 'stream' else 0
-        d.reserved0 = int(os.environ.get('D3R_ALIGN_FLAGS', '0'))   # debug A/B switches of the streaming kernel
         d.stream_grid, d.stream_ppt, d.stream_window, d.n_items = self.stream_grid, self.stream_ppt, self.stream_window, self.n_items
         if self.kernel == 'stream':
             d.items, d.warp_item_ptr = self._items.data_ptr(), self._warp_item_ptr.data_ptr()

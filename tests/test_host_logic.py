@@ -206,3 +206,46 @@ def test_find_reciprocal_matches_host_path_matches_live_reference():
     P2 = np.concatenate((P1[:400] + 0.01 * rng.standard_normal((400, 3)).astype(np.float32), rng.standard_normal((150, 3)).astype(np.float32)))
     a, b = ref(P1, P2), mine(P1, P2)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and int(a[2]) == int(b[2]) > 300
+
+
+def test_load_model_and_from_pretrained_on_a_reference_format_checkpoint(tmp_path):
+    """dust3r/model.py:27-43, 76-85: a checkpoint is {'args': Namespace(model="AsymmetricCroCo3DStereo(...)"), 'model': state
+    dict}; load_model rebuilds the network from the constructor string (ManyAR_PatchEmbed -> PatchEmbedDust3R,
+    landscape_only forced to False) and loads the weights; from_pretrained(path) of an existing file does the same.  No real
+    checkpoint is available offline: a small synthetic one is written in that format (and read back by the live reference's
+    own load_model when it is mounted)."""
+    import argparse
+    from conftest import has_reference
+    from dust3r_b200.config import ModelConfig
+    from dust3r_b200.model import AsymmetricCroCo3DStereo, load_model
+    from dust3r_b200.utils.synth import synth_state_dict
+    cfg = ModelConfig(img_size=(96, 96), enc_embed_dim=192, enc_depth=3, enc_num_heads=3, dec_embed_dim=128, dec_depth=2,
+                      dec_num_heads=2, head_type='linear', landscape_only=False)
+    sd = synth_state_dict(cfg, seed=4)
+    ctor = ("AsymmetricCroCo3DStereo(pos_embed='RoPE100', patch_embed_cls='ManyAR_PatchEmbed', img_size=(96, 96), head_type='linear', "
+            "output_mode='pts3d', depth_mode=('exp', -inf, inf), conf_mode=('exp', 1, inf), enc_embed_dim=192, enc_depth=3, "
+            "enc_num_heads=3, dec_embed_dim=128, dec_depth=2, dec_num_heads=2)")
+    path = str(tmp_path / 'synthetic_checkpoint.pth')
+    # released checkpoints predate dec_blocks2 in some cases: drop them so that the duplication rule (model.py:91-98) is exercised
+    stored = {k: v for k, v in sd.items() if not k.startswith('dec_blocks2')}
+    torch.save({'args': argparse.Namespace(model=ctor), 'model': stored}, path)
+    net = load_model(path, 'cpu', verbose=False)
+    assert isinstance(net, AsymmetricCroCo3DStereo) and net.landscape_only is False
+    got = net.state_dict()
+    assert set(got) == set(sd)
+    for k, v in sd.items():
+        src = sd[k.replace('dec_blocks2', 'dec_blocks')] if k.startswith('dec_blocks2') else v
+        assert torch.equal(got[k], src), k
+    net2 = AsymmetricCroCo3DStereo.from_pretrained(path)
+    assert all(torch.equal(a, b) for a, b in zip(net2.state_dict().values(), got.values()))
+    if has_reference():
+        import sys
+        sys.path.insert(0, '/root/reference')
+        from dust3r.model import load_model as ref_load_model
+        # torch >= 2.6 defaults torch.load to weights_only=True, which rejects the Namespace every DUSt3R checkpoint stores:
+        # allow it for the reference's own (unmodified) loader
+        with torch.serialization.safe_globals([argparse.Namespace]):
+            ref = ref_load_model(path, 'cpu', verbose=False)
+        rsd = ref.state_dict()
+        assert set(rsd) == set(got)
+        assert all(torch.equal(rsd[k], got[k]) for k in got)
