@@ -94,7 +94,9 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   const int max_clusters = num_sms() / 2;
   const int clusters = cluster_tiles < max_clusters ? cluster_tiles : max_clusters;
   const char* tag = (p.mode == 1) ? ((p.flags & F_HEAD_FINAL) ? "conv3x3_head_tail_2cta" : "conv3x3_tcgen05_2cta")
-                                  : (BN == 256 ? "gemm_tcgen05_2cta_bn256" : "gemm_tcgen05_2cta_bn128");
+                                  : (BN == 256 ? (p.K >= 1024 ? "gemm_tcgen05_2cta_bn256" : "gemm_tcgen05_2cta_bn256_shortk")
+                                               : "gemm_tcgen05_2cta_bn128");   // short-K projections (decoder K = 768, DPT K = 256)
+                                                                               // are epilogue-bound: a class of their own in the breakdown
   char detail[96];
   snprintf(detail, sizeof(detail), "M=%d N=%d K=%d flags=0x%x mode=%d epi=%d", p.M, p.N, p.K, (unsigned)p.flags, p.mode, EPI);
   prof::Scope scope(tag, st, 2.0 * double(p.M) * double(p.N) * double(p.K), 0.0, 1, detail);

