@@ -1,10 +1,8 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gemm_gpu.py tests/test_align_gpu.py -x -q 2>&1 | tail -2
-(time timeout 900 python bench.py) > gpurun_out/r02_bench_v7.json 2> gpurun_out/bench.err; python - <<'PY'
+timeout 600 python -m pytest tests/test_multigpu.py -m gpu -x -q 2>&1 | tail -2
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/r02_bench_2gpu_v2.json 2> gpurun_out/b2.err; python - <<'PY'
 import json
-d=json.load(open('gpurun_out/r02_bench_v7.json'))
-print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['whole_step']['frac'], d['roofline']['kernel'], d['roofline']['frac'], d['roofline']['share_of_step'])
-for k,v in list(d['kernels'].items())[:9]: print(k, v['ms'], v['tflops'], v['gbs'])
-for k in ('cloud_opt','cloud_opt_config5'):
-    c=d.get(k); print(k, c['value'], c['roofline']['frac'], c['roofline']['traffic'], c.get('e2e',{}).get('value'))
+d=json.load(open('gpurun_out/r02_bench_2gpu_v2.json'))
+print(d['value'], d['ms_per_step'], d['n_gpus'], d['e2e']['value'], d['clocks'])
 PY
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 scripts/config5_pipeline.py 50 2>/dev/null | tail -1
