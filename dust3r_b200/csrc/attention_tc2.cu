@@ -460,12 +460,11 @@ int attention_hd64_tc2(const void* q, long long ldq, const void* k, long long ld
 template <int ABL, int POLY>
 static int launch_tc2(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, void* out, long long ldo, int B, int heads,
                       int Nq, int Nk, float scale, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr_devices = 0;
+  if (first_launch_on_this_device(attr_devices)) {
     D3R_CUDA(cudaFuncSetAttribute(tc2::attention_tc2_kernel<ABL, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kSmemBytes));
     // two CTAs per SM only fit with the maximum shared-memory carve-out
     D3R_CUDA(cudaFuncSetAttribute(tc2::attention_tc2_kernel<ABL, POLY>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr = true;
   }
   const int total_tiles = ((Nq + tc2::BQ - 1) / tc2::BQ) * heads * B;
   const int slots = 2 * num_sms();   // two persistent CTAs per SM

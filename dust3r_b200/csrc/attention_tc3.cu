@@ -443,10 +443,12 @@ void set_tc3_ablation(int a) { g_tc3_ablation = a; }
 template <int ABL, int POLY>
 static int launch_tc3(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, void* out, long long ldo, int B, int heads,
                       int Nq, int Nk, float scale, cudaStream_t st) {
-  // per device: a process may drive several GPUs and the opt-in is a per-context function attribute
-  D3R_CUDA(cudaFuncSetAttribute(tc3::attention_tc3_kernel<ABL, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::kSmemBytes));
-  // two CTAs per SM only fit with the maximum shared-memory carve-out
-  D3R_CUDA(cudaFuncSetAttribute(tc3::attention_tc3_kernel<ABL, POLY>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  static unsigned long long attr_devices = 0;
+  if (first_launch_on_this_device(attr_devices)) {
+    D3R_CUDA(cudaFuncSetAttribute(tc3::attention_tc3_kernel<ABL, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::kSmemBytes));
+    // two CTAs per SM only fit with the maximum shared-memory carve-out
+    D3R_CUDA(cudaFuncSetAttribute(tc3::attention_tc3_kernel<ABL, POLY>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  }
   const int total_tiles = ((Nq + tc3::BQ - 1) / tc3::BQ) * heads * B;
   const int slots = 2 * num_sms();   // two persistent CTAs per SM
   // equal number of tiles per CTA where possible: a grid of `slots` CTAs would leave a ragged last round

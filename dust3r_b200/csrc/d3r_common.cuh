@@ -48,4 +48,15 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 int num_sms();
 
+// cudaFuncSetAttribute is per device / context: a launch site keeps one bit per device in a static mask and opts in the first time it
+// launches on each device of the process (a process may drive several GPUs: global_aligner(out, 'cuda:1') next to a model on cuda:0)
+inline bool first_launch_on_this_device(unsigned long long& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
 }  // namespace d3r

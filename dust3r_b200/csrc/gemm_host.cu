@@ -56,11 +56,9 @@ int pick_block_n(int N, uint32_t flags) {
 
 template <int BN, int EPI>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const Params& p, int total_tiles, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devices = 0;
+  if (first_launch_on_this_device(attr_devices))
     D3R_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, EPI>::kSmemBytes));
-    attr_set = true;
-  }
   int grid = total_tiles < num_sms() ? total_tiles : num_sms();
   const char* tag = (p.mode == 1) ? ((p.flags & F_HEAD_FINAL) ? "conv3x3_head_tail" : "conv3x3_tcgen05")
                                   : (BN == 256 ? "gemm_tcgen05_bn256" : (BN == 128 ? "gemm_tcgen05_bn128" : "gemm_tcgen05_bn64"));
@@ -85,11 +83,9 @@ bool use_pair(int bn, int num_kb) { return bn >= 128 && (g_impl == 1 || (g_impl 
 template <int BN, int EPI>
 static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const Params& p, int m_tiles, int n_tiles,
                    cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devices = 0;
+  if (first_launch_on_this_device(attr_devices))
     D3R_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN, EPI>::kSmemBytes));
-    attr_set = true;
-  }
   const int cluster_tiles = ((m_tiles + 1) / 2) * n_tiles;
   const int max_clusters = num_sms() / 2;
   const int clusters = cluster_tiles < max_clusters ? cluster_tiles : max_clusters;

@@ -68,3 +68,34 @@ def test_inference_sharded_two_gpus_equals_single_gpu():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert all(ok for _, ok in got), got
+
+
+@pytest.mark.timeout(900)
+def test_two_devices_driven_by_one_process():
+    """One process, two GPUs, current device left at cuda:0: the forward and the aligner on cuda:1 must use cuda:1's stream, set
+    their function attributes there too (they are per device) and give the bits cuda:0 gives."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from test_forward_gpu import _build, _small_cfgs
+    from dust3r_b200.utils.synth import synth_images, synth_pair_predictions
+    from dust3r_b200.cloud_opt import global_aligner
+    cfg, H, W = _small_cfgs()['small_dpt']
+    imgs = synth_images(2, H, W, seed=5)
+    res, losses = [], []
+    n = 3
+    edges = [(i, j) for i in range(n) for j in range(n) if i != j]
+    out = synth_pair_predictions(n, edges, 32, 48, seed=0)
+    torch.cuda.set_device(0)
+    for d in (0, 1):
+        dev = torch.device('cuda', d)
+        net, _ = _build(cfg, 11, dev)
+        r1, r2 = net(dict(img=imgs[0]['img'].to(dev), instance=['0']), dict(img=imgs[1]['img'].to(dev), instance=['1']))
+        res.append((r1['pts3d'].cpu(), r2['conf'].cpu()))
+        torch.manual_seed(0)
+        scene = global_aligner(out, dev, verbose=False)
+        scene.compute_global_alignment(init=None, niter=20)
+        losses.append(scene.last_losses.cpu())
+        assert torch.cuda.current_device() == 0
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    assert torch.equal(losses[0], losses[1]) and bool(torch.isfinite(losses[1]).all())
