@@ -78,6 +78,9 @@ def _declare(lib):
     lib.d3r_weiszfeld_focal.argtypes = [i32, i32, i32, vp, vp, i32, vp, vp]
     lib.d3r_nearest_neighbours.restype = C.c_int
     lib.d3r_nearest_neighbours.argtypes = [i32, i32, vp, vp, vp, vp]
+    lib.d3r_image_resize_crop_normalize.restype = C.c_int
+    lib.d3r_image_resize_crop_normalize.argtypes = [vp, i32, i32, i32, i32, vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32,
+                                                    vp, vp, vp, vp]
     for name in ('d3r_sizeof_align_item', 'd3r_sizeof_pack_entry', 'd3r_align_stream_slots_per_item',
                  'd3r_align_stream_warps_per_cta', 'd3r_align_stream_max_window'):
         getattr(lib, name).restype = C.c_int

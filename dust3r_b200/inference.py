@@ -94,6 +94,14 @@ def _fill_pinned(dst, tensors, row0, wait=True):
     return r, futs
 
 
+def _uploadable(t, dev):
+    """Sources the copy stream can read directly: pinned host memory, or an image that already lives on the target GPU
+    (load_images(..., device=...): resized and normalised there)."""
+    if not t.is_cuda:
+        return t.is_pinned()
+    return t.device.index == (dev.index if dev.index is not None else torch.cuda.current_device())
+
+
 def _micro_batch(batch_size):
     """Pairs per fused forward call.  A user batch of >= 16 pairs is run as two halves so that the host-side
     staging + H2D of one half and the D2H of the other overlap the GPU compute (per-pair results do not depend on
@@ -164,7 +172,7 @@ def inference(pairs, model, device, batch_size=8, verbose=True, keep_on_device=F
             uniq_dev = torch.empty((len(order),) + tuple(order[0].shape[1:]), dtype=order[0].dtype, device=dev)
             up.wait_stream(main)
             with torch.cuda.stream(up):
-                if all(t.is_pinned() for t in order):
+                if all(_uploadable(t, dev) for t in order):
                     for j, t in enumerate(order):
                         uniq_dev[j:j + 1].copy_(t, non_blocking=True)
                 else:
@@ -174,14 +182,14 @@ def inference(pairs, model, device, batch_size=8, verbose=True, keep_on_device=F
             ev_uniq = torch.cuda.Event()
             ev_uniq.record(up)
             main.wait_event(ev_uniq)
-    all_pinned = all(v['img'].is_pinned() for vs in views for v in vs)
+    all_pinned = all(_uploadable(v['img'], dev) for vs in views for v in vs)
     if return_images or not (uniq_dev is not None or all_pinned):
         img_pin = [torch.empty((rows[k],) + tuple(proto[k].shape[1:]), dtype=proto[k].dtype, pin_memory=True) for k in range(2)]
     for i in tqdm.trange(0, n, mb, disable=not verbose):
         chunk = (views[0][i:i + mb], views[1][i:i + mb])
         r1 = r0
         srcs = [[v['img'] for v in chunk[k]] for k in range(2)]
-        direct = all(t.is_pinned() for ts in srcs for t in ts)
+        direct = all(_uploadable(t, dev) for ts in srcs for t in ts)
         indexed = uniq_dev is not None
         for k in range(2):
             # sources already in pinned memory are uploaded straight from where they are; the collated copy that the

@@ -143,3 +143,24 @@ def many_ar_inputs(H: int, W: int, seed: int = 9):
     ts2 = torch.tensor([L, P, L, P], dtype=torch.int32)
     return (dict(img=img1, true_shape=ts1, instance=['0', '1', '2', '3']),
             dict(img=img2, true_shape=ts2, instance=['4', '5', '6', '7']))
+
+
+def synth_photo(H: int, W: int, seed: int = 0):
+    """A decoded 'photograph': uint8 (H, W, 3) numpy array with natural-image statistics (smooth colour fields, a few hard
+    edges, sensor noise) -- input of the load_images preprocessing tests (edges and noise exercise the negative lobes and the
+    clipping of the resampling filters, which flat or purely random images do not)."""
+    g = _gen(seed, f'photo{H}x{W}')
+    y = torch.linspace(0, 1, H)[:, None, None]
+    x = torch.linspace(0, 1, W)[None, :, None]
+    f = torch.rand((6, 3), generator=g) * 9 + 1
+    p = torch.rand((6, 3), generator=g) * 6.28
+    field = sum(torch.sin(f[k] * (x if k % 2 else y) * 6.28 + p[k]) for k in range(6)) / 6
+    img = 127 + 110 * field
+    # hard-edged rectangles (saturated values next to dark ones: ringing gets clipped)
+    for _ in range(4):
+        r = torch.rand((4,), generator=g)
+        y0, x0 = int(r[0] * H * 0.8), int(r[1] * W * 0.8)
+        y1, x1 = y0 + 1 + int(r[2] * H * 0.3), x0 + 1 + int(r[3] * W * 0.3)
+        img[y0:y1, x0:x1] = torch.randint(0, 2, (3,), generator=g).to(torch.float32) * 255
+    img = img + torch.randn((H, W, 3), generator=g) * 12
+    return img.clamp(0, 255).to(torch.uint8).numpy()

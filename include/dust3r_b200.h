@@ -280,6 +280,20 @@ int d3r_weiszfeld_focal(int32_t n_maps, int32_t H, int32_t W, const float* pts3d
  * tie): the two tree queries of find_reciprocal_matches (dust3r/utils/geometry.py:345-361), brute force on the GPU. */
 int d3r_nearest_neighbours(int32_t n_queries, int32_t n_points, const float* queries_dev, const float* points_dev, int32_t* nn_dev,
                            void* stream);
+/* Per-image pixel work of load_images (dust3r/utils/image.py:62-71 `_resize_pil_image`, :101-124 crop + ImgNorm): Pillow's 8-bit
+ * Image.resize (src/libImaging/Resample.c: horizontal then vertical pass, 22-bit fixed-point coefficients, each pass rounded and
+ * clipped to uint8), the centre crop, and torchvision's ToTensor + Normalize(0.5, 0.5), bit-exact.
+ *   src [H0][W0][3] uint8 RGB (decoded image)            ->  out [3][H2][W2] fp32 in [-1, 1]
+ *   x/ybounds [W1 | H1][2] = (first source index, taps), x/ycoefs [W1 | H1][kx | ky] int32 with 22 fractional bits: the tables of
+ *   Resample.c precompute_coeffs + normalize_coeffs_8bpc for W0 -> W1 and H0 -> H1 (a dimension that does not change gets the
+ *   identity table: bounds (i, 1), coefficient 1 << 22); the output is the window [crop_y0, crop_y0 + H2) x [crop_x0, crop_x0 + W2)
+ *   of the resized image; [row0, row0 + rows) = the source rows those output rows read (union of their ybounds);
+ *   lut [256] = the fp32 value of every byte after ImgNorm; tmp = workspace of rows * W2 * 3 bytes. */
+int d3r_image_resize_crop_normalize(const uint8_t* src_dev, int32_t H0, int32_t W0, int32_t H1, int32_t W1,
+                                    const int32_t* xbounds_dev, const int32_t* xcoefs_dev, int32_t kx,
+                                    const int32_t* ybounds_dev, const int32_t* ycoefs_dev, int32_t ky, int32_t row0, int32_t rows,
+                                    int32_t crop_x0, int32_t crop_y0, int32_t H2, int32_t W2, const float* lut_dev, uint8_t* tmp_dev,
+                                    float* out_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Path 1 — pairwise forward: replaces AsymmetricCroCo3DStereo.forward (dust3r/model.py:199-211 =

@@ -185,8 +185,43 @@ def align_goldens():
     np.savez_compressed(os.path.join(HERE, 'align_n4.npz'), **res)
 
 
+IMAGE_CASES = [  # (H, W, seed, size, square_ok): shrinking (Lanczos) and enlarging (bicubic), both orientations, squares
+    (150, 200, 1, 128, False), (200, 150, 2, 128, False), (130, 130, 3, 128, False), (130, 130, 3, 128, True),
+    (37, 53, 4, 224, False), (300, 170, 5, 224, False), (200, 300, 6, 256, False), (90, 70, 7, 160, False),
+]
+
+
+def image_goldens():
+    """load_images of the UNMODIFIED reference (PIL resize / crop + torchvision ImgNorm) on synthetic photographs written
+    as PNG files.  The fixture holds the decoded inputs and the reference's outputs; an output has only 256 possible
+    values per element ((v / 255 - 0.5) / 0.5), so it is stored as the byte v after checking that the map is exact."""
+    import tempfile
+    import PIL.Image
+    from dust3r.utils.image import load_images
+    from dust3r_b200.utils.synth import synth_photo
+    lut = torch.arange(256, dtype=torch.uint8).to(torch.float32).div(255).sub_(0.5).div_(0.5)
+    res = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for k, (H, W, seed, size, square_ok) in enumerate(IMAGE_CASES):
+            photo = synth_photo(H, W, seed)
+            path = os.path.join(tmp, f'{k}.png')
+            PIL.Image.fromarray(photo).save(path)
+            view = load_images([path], size=size, square_ok=square_ok, verbose=False)[0]
+            img = view['img'][0]                                     # (3, H2, W2) float32
+            v = torch.round((img * 0.5 + 0.5) * 255).to(torch.uint8)
+            assert torch.equal(lut[v.long()], img), 'reference output is not one of the 256 normalised byte values'
+            res[f'{k}|in'] = photo
+            res[f'{k}|out_u8'] = v.permute(1, 2, 0).contiguous().numpy()
+            res[f'{k}|true_shape'] = view['true_shape']
+            res[f'{k}|args'] = np.int64([size, int(square_ok)])
+            print('image', k, (H, W), '->', tuple(img.shape), 'size', size)
+    np.savez_compressed(os.path.join(HERE, 'load_images.npz'), **res)
+
+
 if __name__ == '__main__':
-    what = sys.argv[1:] or ['pairs', 'align', 'forward']
+    what = sys.argv[1:] or ['pairs', 'align', 'forward', 'images']
+    if 'images' in what:
+        image_goldens()
     with torch.no_grad():
         if 'pairs' in what:
             pair_goldens()
