@@ -242,6 +242,55 @@ def cloud_opt_config5_section(device, pk, n=50, niter=300):
     return res
 
 
+def load_images_section(device, pk, reps=20):
+    """the pixel work of load_images for one 12 Mpx photograph (4000x3000 -> 512x384): Pillow's two-pass
+    resize + crop + ImgNorm on the GPU (d3r_image_resize_crop_normalize) against the same work done by PIL on a host core
+    (what the reference does), checked bit for bit.  `value` has the decoded bytes resident in HBM, `e2e` uploads them
+    (pageable numpy array, as PIL hands them over) inside the timed region."""
+    import PIL.Image
+    from dust3r_b200.utils import image as im
+    from dust3r_b200.utils.synth import synth_photo
+    h0, w0, size = 3000, 4000, 512
+    photo = synth_photo(h0, w0, seed=0)
+    plan = im.preprocess_plan(h0, w0, size)
+    src = torch.from_numpy(photo).to(device)
+    for _ in range(3):
+        out = im.preprocess_image_u8(src, size, device=device)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = im.preprocess_image_u8(src, size, device=device)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    t0 = time.perf_counter()
+    for _ in range(5):
+        out_h = im.preprocess_image_u8(photo, size, device=device)
+    torch.cuda.synchronize()
+    ms_e2e = (time.perf_counter() - t0) / 5 * 1e3
+    # host pipeline of the reference on the same decoded image
+    pil = PIL.Image.fromarray(photo)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        r = im._rescale(pil, size)
+        r = r.crop(im._crop_box(r.size[0], r.size[1], size, False))
+        ref = ((torch.from_numpy(np.asarray(r, dtype=np.float32) / 255).permute(2, 0, 1) - 0.5) / 0.5)[None]
+    ms_cpu = (time.perf_counter() - t0) / 3 * 1e3
+    by = 3 * plan['rows'] * w0 + 2 * 3 * plan['rows'] * plan['w2'] + 12 * plan['h2'] * plan['w2']
+    gbs = by / ms / 1e6
+    return dict(metric='load_images pixel work, images/sec', value=1e3 / ms, unit='images/s', ms_per_image=ms,
+                config=dict(workload=f'{w0}x{h0} RGB uint8 -> {plan["w2"]}x{plan["h2"]} fp32 CHW (Lanczos, crop, ImgNorm), decoded bytes resident in HBM'),
+                bit_exact_vs_host_pipeline=bool(torch.equal(out.cpu(), ref) and torch.equal(out_h.cpu(), ref)),
+                roofline=dict(bound='hbm', achieved=gbs, peak=pk['hbm'], unit='GB/s', frac=gbs / pk['hbm'], traffic=None,
+                              algorithmic_bytes_per_image=by, peak_source=pk['source'],
+                              note='two launches + host-side table lookup per image; timed with CUDA events over back-to-back calls'),
+                e2e=dict(value=1e3 / ms_e2e, unit='images/s', ms_per_image=ms_e2e, h2d_bytes_per_image=int(photo.nbytes),
+                         includes='H2D of the decoded uint8 image from pageable host memory'),
+                cpu_baseline=dict(value=1e3 / ms_cpu, unit='images/s', ms_per_image=ms_cpu, cores=1, kind='reference',
+                                  sample='PIL.Image.resize(LANCZOS) + crop + ImgNorm of the same image, 3 repeats (the library calls the reference makes)'))
+
+
 def _oracle_forward_setup(threads):
     from dust3r_b200.config import vitl_512_dpt
     from dust3r_b200.utils.synth import synth_state_dict, synth_images
@@ -536,6 +585,10 @@ def main():
             line['cloud_opt_config5'] = cloud_opt_config5_section(device, pk)
         except torch.cuda.OutOfMemoryError as ex:      # 16 GB of observations: needs a mostly free GPU
             line['cloud_opt_config5'] = dict(unavailable=f'out of memory: {ex}')
+        try:
+            line['load_images'] = load_images_section(device, pk)
+        except Exception as ex:                        # an extra leg must never cost the headline line
+            line['load_images'] = dict(unavailable=f'{type(ex).__name__}: {ex}')
     if world == 1 and not args.skip_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline_forward(1)
         if not args.skip_cloud_opt:
