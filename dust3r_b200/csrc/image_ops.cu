@@ -1,8 +1,10 @@
 // Image preprocessing of load_images on the GPU (dust3r/utils/image.py:62-71, 101-124): the decoded 8-bit RGB
 // image is uploaded ONCE as bytes (3 B / source pixel instead of PIL resizing on a host core and 12 B / output pixel going up) and
 // Pillow's two-pass fixed-point resampling, the centre crop and ImgNorm run in HBM.  Integer / byte work, HBM-bound and tiny
-// (36 MB for a 12 Mpx photo): one thread per output element, byte loads through L1 (neighbouring threads share their windows),
-// coalesced stores; no tensor cores, no shared-memory staging needed at this size.  The per-thread bodies live in
+// (36 MB for a 12 Mpx photo): one thread per output PIXEL (three accumulators share every coefficient load), consecutive threads
+// on consecutive columns so that a warp's loads of a tap cover one contiguous stretch of a row (overlapping windows of neighbouring
+// outputs are served by L1), tap-major coefficient tables (coalesced / broadcast loads), coalesced stores; the 4.6 MB intermediate
+// image never leaves the 126 MB L2.  No tensor cores, no shared-memory staging needed at this size.  The per-thread bodies live in
 // resample_core.h so that the host test harness runs the same code (bit-exact against Pillow without a GPU).
 #include "d3r_common.cuh"
 #include "prof.h"
@@ -41,18 +43,18 @@ extern "C" int d3r_image_resize_crop_normalize(const uint8_t* src_dev, int32_t H
                 W1, H1);
   D3R_CHECK_ARG(row0 >= 0 && rows > 0 && row0 + rows <= H0, "d3r_image_resize_crop_normalize: source rows [%d, %d) outside [0, %d)",
                 row0, row0 + rows, H0);
-  const long long n_tmp = (long long)rows * W2 * 3, n_out = 3ll * H2 * W2;
+  const long long n_tmp = (long long)rows * W2, n_out = (long long)H2 * W2;    // pixels = threads of the two launches
   D3R_CHECK_ARG(n_tmp < (1ll << 31) * kThreads && n_out < (1ll << 31) * kThreads, "d3r_image_resize_crop_normalize: image too large");
   cudaStream_t st = (cudaStream_t)stream;
   {
-    HorizontalArgs a{src_dev, W0, row0, rows, crop_x0, W2, xbounds_dev, xcoefs_dev, kx, tmp_dev};
-    prof::Scope scope("image_resample_h", st, 0.0, double(rows) * W0 * 3 + double(n_tmp), 1);
+    HorizontalArgs a{src_dev, W0, row0, rows, crop_x0, W2, W1, xbounds_dev, xcoefs_dev, tmp_dev};
+    prof::Scope scope("image_resample_h", st, 0.0, 3.0 * (double(rows) * W0 + double(n_tmp)), 1);
     horizontal_kernel<<<(unsigned)((n_tmp + kThreads - 1) / kThreads), kThreads, 0, st>>>(a);
     D3R_LAUNCH_CHECK();
   }
   {
-    VerticalArgs a{tmp_dev, row0, W2, ybounds_dev, ycoefs_dev, ky, crop_y0, H2, W2, lut_dev, out_dev};
-    prof::Scope scope("image_resample_v", st, 0.0, double(n_tmp) + 4.0 * double(n_out), 1);
+    VerticalArgs a{tmp_dev, row0, W2, H1, ybounds_dev, ycoefs_dev, crop_y0, H2, W2, lut_dev, out_dev};
+    prof::Scope scope("image_resample_v", st, 0.0, 3.0 * double(n_tmp) + 12.0 * double(n_out), 1);
     vertical_kernel<<<(unsigned)((n_out + kThreads - 1) / kThreads), kThreads, 0, st>>>(a);
     D3R_LAUNCH_CHECK();
   }

@@ -184,7 +184,8 @@ def _device_table(dev, in_size, out_size, method):
         if len(_DEVICE_TABLES) > 512:
             _DEVICE_TABLES.clear()
         bounds, coefs = resample_table(in_size, out_size, method)
-        hit = (torch.from_numpy(bounds).to(dev), torch.from_numpy(coefs).to(dev), int(coefs.shape[1]))
+        # the kernels read the coefficients tap-major ([ksize][out_size]): neighbouring threads, neighbouring words
+        hit = (torch.from_numpy(bounds).to(dev), torch.from_numpy(np.ascontiguousarray(coefs.T)).to(dev), int(coefs.shape[1]))
         _DEVICE_TABLES[key] = hit
     return hit
 

@@ -284,9 +284,9 @@ int d3r_nearest_neighbours(int32_t n_queries, int32_t n_points, const float* que
  * Image.resize (src/libImaging/Resample.c: horizontal then vertical pass, 22-bit fixed-point coefficients, each pass rounded and
  * clipped to uint8), the centre crop, and torchvision's ToTensor + Normalize(0.5, 0.5), bit-exact.
  *   src [H0][W0][3] uint8 RGB (decoded image)            ->  out [3][H2][W2] fp32 in [-1, 1]
- *   x/ybounds [W1 | H1][2] = (first source index, taps), x/ycoefs [W1 | H1][kx | ky] int32 with 22 fractional bits: the tables of
- *   Resample.c precompute_coeffs + normalize_coeffs_8bpc for W0 -> W1 and H0 -> H1 (a dimension that does not change gets the
- *   identity table: bounds (i, 1), coefficient 1 << 22); the output is the window [crop_y0, crop_y0 + H2) x [crop_x0, crop_x0 + W2)
+ *   x/ybounds [W1 | H1][2] = (first source index, taps <= kx | ky), x/ycoefs [kx | ky][W1 | H1] (tap-major) int32 with 22
+ *   fractional bits: the tables of Resample.c precompute_coeffs + normalize_coeffs_8bpc for W0 -> W1 and H0 -> H1 (a dimension
+ *   that does not change gets the identity table: bounds (i, 1), coefficient 1 << 22); the output is the window [crop_y0, crop_y0 + H2) x [crop_x0, crop_x0 + W2)
  *   of the resized image; [row0, row0 + rows) = the source rows those output rows read (union of their ybounds);
  *   lut [256] = the fp32 value of every byte after ImgNorm; tmp = workspace of rows * W2 * 3 bytes. */
 int d3r_image_resize_crop_normalize(const uint8_t* src_dev, int32_t H0, int32_t W0, int32_t H1, int32_t W1,

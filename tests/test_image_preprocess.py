@@ -137,7 +137,8 @@ def _run_on_host(lib, photo, size, square_ok):
     tmp = np.full((plan['rows'], plan['w2'], 3), 0xAB, dtype=np.uint8)
     out = np.full((1, 3, plan['h2'], plan['w2']), np.nan, dtype=np.float32)
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-    rc = lib.resample_host(p(src), h0, w0, plan['h1'], plan['w1'], p(xb), p(xk), xk.shape[1], p(yb), p(yk), yk.shape[1],
+    xk_t, yk_t = np.ascontiguousarray(xk.T), np.ascontiguousarray(yk.T)          # tap-major, as uploaded by _device_table
+    rc = lib.resample_host(p(src), h0, w0, plan['h1'], plan['w1'], p(xb), p(xk_t), xk.shape[1], p(yb), p(yk_t), yk.shape[1],
                            plan['row0'], plan['rows'], plan['left'], plan['upper'], plan['h2'], plan['w2'], p(lut), p(tmp), p(out))
     assert rc == 0
     return out, plan
