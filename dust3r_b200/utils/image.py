@@ -78,36 +78,69 @@ def _open_rgb(path):
     return exif_transpose(PIL.Image.open(path)).convert('RGB')
 
 
-def load_images(folder_or_list, size, square_ok=False, verbose=True, patch_size=16, device=None):
+def _host_view(pil, size, square_ok, patch_size):
+    """The reference's per-image pipeline on a decoded PIL image: resize, centre crop, ImgNorm -> (1, 3, H, W) CPU tensor."""
+    w_in, h_in = pil.size
+    # 224 models: the SHORT edge becomes 224 (then a square crop); the others: the long edge becomes `size`
+    long_edge = round(size * max(w_in / h_in, h_in / w_in)) if size == 224 else size
+    pil = _rescale(pil, long_edge)
+    pil = pil.crop(_crop_box(pil.size[0], pil.size[1], size, square_ok, patch_size))
+    pixels = torch.from_numpy(np.asarray(pil, dtype=np.float32) / 255).permute(2, 0, 1)
+    return ((pixels - 0.5) / 0.5)[None]
+
+
+def load_images(folder_or_list, size, square_ok=False, verbose=True, patch_size=16, device=None, workers=None):
     """Folder name or list of file names -> list of dict(img (1,3,H,W) in [-1,1], true_shape int32 [[H,W]], idx,
     instance) ready for make_pairs / inference.  Files that are not .jpg/.jpeg/.png are skipped.
     device=None: the reference's host pipeline, `img` is a CPU tensor.  device=<a B200>: decode on the host, resize / crop /
-    normalise on that GPU (same bits), `img` is resident there."""
+    normalise on that GPU (same bits), `img` is resident there.
+    Files are decoded (device=None: decoded, resized and normalised) by `workers` threads -- PIL releases the GIL in its codecs
+    and resampling loops -- while the results are consumed in file order, so idx / instance / verbose output are those of the
+    reference's sequential loop; default min(8, cores), workers=1 is strictly sequential."""
     if isinstance(folder_or_list, str):
         root, names = folder_or_list, sorted(os.listdir(folder_or_list))
     elif isinstance(folder_or_list, list):
         root, names = '', folder_or_list
     else:
         raise ValueError(f'bad {folder_or_list=} ({type(folder_or_list)})')
-    views = []
-    for name in names:
-        if not name.lower().endswith(_EXTENSIONS):
-            continue
+    names = [name for name in names if name.lower().endswith(_EXTENSIONS)]
+
+    def host_stage(name):
         pil = _open_rgb(os.path.join(root, name))
-        w_in, h_in = pil.size
         if device is None:
-            # 224 models: the SHORT edge becomes 224 (then a square crop); the others: the long edge becomes `size`
-            long_edge = round(size * max(w_in / h_in, h_in / w_in)) if size == 224 else size
-            pil = _rescale(pil, long_edge)
-            pil = pil.crop(_crop_box(pil.size[0], pil.size[1], size, square_ok, patch_size))
-            pixels = torch.from_numpy(np.asarray(pil, dtype=np.float32) / 255).permute(2, 0, 1)
-            img = ((pixels - 0.5) / 0.5)[None]
-        else:
-            img = preprocess_image_u8(np.array(pil, dtype=np.uint8), size, square_ok, device, patch_size)
+            return pil.size, _host_view(pil, size, square_ok, patch_size)
+        return pil.size, np.array(pil, dtype=np.uint8)
+
+    if workers is None:
+        workers = min(8, os.cpu_count() or 1)
+    workers = max(1, min(int(workers), len(names)))
+    views = []
+
+    def consume(name, staged):
+        (w_in, h_in), item = staged
+        img = item if device is None else preprocess_image_u8(item, size, square_ok, device, patch_size)
         h_out, w_out = int(img.shape[-2]), int(img.shape[-1])
         if verbose:
             print(f' - adding {name} with resolution {w_in}x{h_in} --> {w_out}x{h_out}')
         views.append(dict(img=img, true_shape=np.int32([[h_out, w_out]]), idx=len(views), instance=str(len(views))))
+
+    if workers == 1:
+        for name in names:
+            consume(name, host_stage(name))
+    else:
+        # at most 2 x workers files in flight (a decoded 12 Mpx photograph is 36 MB), consumed strictly in file order
+        from collections import deque
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=workers) as pool:
+            window, todo = deque(), iter(names)
+            for name in todo:
+                window.append((name, pool.submit(host_stage, name)))
+                if len(window) >= 2 * workers:
+                    first, fut = window.popleft()
+                    consume(first, fut.result())
+            while window:
+                first, fut = window.popleft()
+                consume(first, fut.result())
     assert views, 'no images found at ' + root
     if verbose:
         print(f' (Found {len(views)} images)')

@@ -171,3 +171,34 @@ def test_preprocess_rejects_bad_input():
     from dust3r_b200 import _lib
     with pytest.raises(_lib.D3RError):
         img_mod.preprocess_image_u8(np.zeros((32, 32, 3), dtype=np.uint8), 512, device='cpu')   # no CPU fallback
+
+
+def test_load_images_folder_threads_keep_the_sequential_contract(tmp_path, capsys):
+    """Decoding on a thread pool must not change anything observable: file order, idx / instance, skipped files, verbose lines."""
+    import PIL.Image
+    shapes = [(90, 120), (120, 90), (100, 100), (64, 200), (33, 47), (150, 151), (80, 81)]
+    for k, (h, w) in enumerate(shapes):
+        PIL.Image.fromarray(synth_photo(h, w, seed=50 + k)).save(os.path.join(str(tmp_path), f'im{k:02d}.{"png" if k % 2 else "jpg"}'))
+    open(os.path.join(str(tmp_path), 'readme.txt'), 'w').write('not an image')
+    seq = img_mod.load_images(str(tmp_path), size=64, verbose=True, workers=1)
+    lines_seq = capsys.readouterr().out
+    for workers in (2, 3, None):
+        par = img_mod.load_images(str(tmp_path), size=64, verbose=True, workers=workers)
+        assert capsys.readouterr().out == lines_seq
+        assert len(par) == len(seq) == len(shapes)
+        for a, b in zip(par, seq):
+            assert torch.equal(a['img'], b['img']) and np.array_equal(a['true_shape'], b['true_shape'])
+            assert a['idx'] == b['idx'] and a['instance'] == b['instance']
+    assert [v['idx'] for v in seq] == list(range(len(shapes))) and lines_seq.count(' - adding im') == len(shapes)
+    if has_reference():
+        sys.path.insert(0, REFERENCE)
+        try:
+            from dust3r.utils.image import load_images as ref_load_images
+        finally:
+            sys.path.remove(REFERENCE)
+        ref = ref_load_images(str(tmp_path), size=64, verbose=False)
+        assert len(ref) == len(seq)
+        for a, b in zip(seq, ref):
+            assert torch.equal(a['img'], b['img']) and np.array_equal(a['true_shape'], b['true_shape']) and a['instance'] == b['instance']
+    with pytest.raises(AssertionError):
+        img_mod.load_images([os.path.join(str(tmp_path), 'readme.txt')], size=64, verbose=False)
