@@ -43,7 +43,8 @@ def get_imshapes(edges, pred_i, pred_j):
     for e, (i, j) in enumerate(edges):
         for img, pts in ((i, pred_i[e]), (j, pred_j[e])):
             hw = (int(pts.shape[0]), int(pts.shape[1]))
-            assert shapes.setdefault(img, hw) == hw, f'incorrect shape for image {img}'
+            seen = shapes.setdefault(img, hw)          # not inside the assert: `python -O` strips those
+            assert seen == hw, f'incorrect shape for image {img}'
     return [shapes.get(img) for img in range(max(shapes) + 1)]
 
 
