@@ -77,6 +77,11 @@ def test_optimizer_host_objects_on_cpu():
         net.compute_global_alignment(init=None, niter=2)
     net2 = global_aligner(out, 'cpu', mode=GlobalAlignerMode.ModularPointCloudOptimizer, verbose=False)
     assert len(net2.im_depthmaps) == n and net2.get_intrinsics().shape == (n, 3, 3)
+    # the opt-in early upload is a no-op off CUDA and never reaches the optimizer's constructor; the caller's dict is untouched
+    torch.manual_seed(0)
+    net3 = global_aligner(out, 'cpu', verbose=False, early_upload=True)
+    assert torch.equal(net3.im_depthmaps, net.im_depthmaps) and torch.equal(net3.pw_poses, net.pw_poses)
+    assert out['pred1']['pts3d'].device.type == 'cpu'
 
 
 @pytest.mark.skipif(not has_reference(), reason='reference not mounted')
